@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- RWR GTEPS on the C2 workload (BASELINE.json configs[1]): single-seed Random Walk with Restart,
+20 power iterations, on a synthetic Twitter-shaped graph (1 M users, 10 M tweets, ~200 M links, power-law degrees).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision fp64|fp32] [--scale S]
+
+A "step" is one pass of the hot path over one seed: init + 20 x (SpMV + fix-up) with the graph resident in HBM.
+  value      GTEPS = nnz(W) x iterations x seeds / time, K steps bracketed by barrier + synchronize, CUDA events on
+             the stream the kernels run on, max over ranks, whole job (all ranks; weak scaling: one seed per rank/step)
+  e2e        same metric through the public API `Recommender.Recommendation(seed, 0.15f, 20, 10)` with host buffers:
+             seed in from the host, top-10 (id, score) pairs back to the host inside the timed region
+  roofline   dominant kernel k_spmv against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (a port: the reference is C#, no toolchain here) on a bounded sample, rank 0, N=1 only
+--impl reference times that CPU oracle alone, with min(10, nproc) threads over independent seeds (Program.cs:11).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_ITER = 20
+TOP_K = 10
+C_FLOAT = 0.15
+
+# C2 / C3 graph: 1 M users + 10 M tweets; 10 M authorship + 76 M like + 21 M friendship
+# relations, two links each, -> ~200 M links after the (source, type, target) dedup.
+C2_SPEC = dict(seed=20260102, n_users=1_000_000, n_items=10_000_000, n_third=0, authorship_per_mille=1000,
+               n_like=76_000_000, n_friend=21_000_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
+               p1_byte=61, reserved=0)
+
+
+def scaled_spec(scale: float) -> dict:
+    s = dict(C2_SPEC)
+    if scale != 1.0:
+        for k in ("n_users", "n_items", "n_like", "n_friend"):
+            s[k] = max(4, int(s[k] * scale))
+    return s
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(n: int, nnz: int, vb: int, layout_index: bool):
+    """E(4+vb) + 4(N+1) + 2 N vb per iteration; and the bytes of the layout actually in HBM."""
+    formula = nnz * (4 + vb) + 4 * (n + 1) + 2 * n * vb
+    if layout_index:   # indices only; per node: row_ptr, inv read, next-x write (y is written on the last iteration only)
+        actual = nnz * 4 + 4 * (n + 1) + 2 * n * vb
+    else:
+        actual = formula
+    return formula, actual
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons of one GPU through NVML while the timed regions run."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:   # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:   # noqa: BLE001
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if isinstance(bit, int) and bit and (mask & bit) == bit and "None" not in name and "All" not in name:
+                        self.reasons.add(name.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:   # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def stop(self) -> dict:
+        self._halt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        # under load = the upper half of the samples (idle gaps between host calls pull the raw median down)
+        s = sorted(self.samples)
+        return {"sm_mhz": statistics.median(s[len(s) // 2:]), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(r for r in self.reasons if r not in ("GpuIdle", "ApplicationsClocksSetting")),
+                "samples": len(s)}
+
+
+def pick_seeds(raw_deg, n_users: int, count: int, offset: int = 0):
+    """Deterministic seed users with a non-trivial neighbourhood: users j*stride with >= 8 raw links."""
+    import numpy as np
+    cand = np.flatnonzero(raw_deg[:n_users] >= 8)
+    if len(cand) == 0:
+        cand = np.flatnonzero(raw_deg[:n_users] > 0)
+    idx = (np.arange(offset, offset + count) * 7919) % len(cand)
+    return cand[idx].astype(np.int32)
+
+
+# ======================================================================================================= ours
+def run_ours(args):
+    import numpy as np
+    import torch
+    import recommendersystems_b200 as rs
+    from recommendersystems_b200 import _native as N
+    from recommendersystems_b200.rwr import run_fixed
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    precision = rs.FP32 if args.precision == "fp32" else rs.FP64
+    vb = 4 if precision == rs.FP32 else 8
+    spec = scaled_spec(args.scale)
+    stream = torch.cuda.current_stream().cuda_stream
+    t0 = time.perf_counter()
+    g = rs.Graph.synthetic(spec, device=local, stream=stream)
+    g.buildGraph()
+    info = g.info()
+    setup_s = time.perf_counter() - t0
+    n, nnz = info.n_nodes, info.nnz
+    raw_deg = g.degrees(raw=True)
+    n_total = args.warmup + args.steps
+    # distinct seeds per rank (weak scaling: every rank runs its own seeds on its replica of the graph)
+    seeds = pick_seeds(raw_deg, spec["n_users"], n_total * 2, offset=rank * n_total * 2)
+    c = rs.widen_float(C_FLOAT)
+
+    # ---- device-resident steps: warm-up, then exactly K timed steps
+    for i in range(args.warmup):
+        run_fixed(g, [int(seeds[i])], c, N_ITER, precision).close()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iter_ms, launches = 0.0, 0
+    barrier()
+    ev0.record()
+    for i in range(args.steps):
+        r = run_fixed(g, [int(seeds[args.warmup + i])], c, N_ITER, precision)
+        ri = r.info()
+        iter_ms += ri.iterate_ms
+        launches += ri.kernel_launches
+        r.close()
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+
+    # ---- end to end through the reference-facing API, host buffers in / out
+    rec = rs.Recommender(g, precision)
+    for i in range(min(args.warmup, 2)):
+        rec.Recommendation(int(seeds[n_total + i]), C_FLOAT, N_ITER, TOP_K)
+    barrier()
+    t0 = time.perf_counter()
+    last_top = None
+    for i in range(args.steps):
+        last_top = rec.Recommendation(int(seeds[n_total + args.warmup + i]), C_FLOAT, N_ITER, TOP_K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3, iter_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, iter_ms = (float(x) for x in times.tolist())
+    edges_total = float(nnz) * N_ITER * args.steps * world
+    value = edges_total / (dev_ms * 1e-3) / 1e9
+    e2e_value = edges_total / (e2e_ms * 1e-3) / 1e9
+
+    line = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel, timed live with CUDA events on its own stream
+        spmv_ms, fix_ms = C.c_float(), C.c_float()
+        rc = N.lib().rwr_profile_iteration(g._h, int(seeds[0]), c, precision, 20, C.byref(spmv_ms), C.byref(fix_ms))
+        if rc != 0:
+            raise RuntimeError(N.last_error())
+        peak, peak_src = measured_peak_gbs()
+        formula_b, actual_b = algorithmic_bytes(n, nnz, vb, info.layout == N.LAYOUT_INDEX)
+        achieved = formula_b / (spmv_ms.value * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get(args.precision, {}).get("dram_bytes_per_launch")
+            except Exception:   # noqa: BLE001
+                traffic = None
+        roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "kernel": "k_spmv", "kernel_ms": round(spmv_ms.value, 4), "fixup_ms": round(fix_ms.value, 4),
+                    "algorithmic_bytes_per_launch": formula_b,
+                    "layout": "index-only (row weight folded into x)" if info.layout == N.LAYOUT_INDEX else "valued",
+                    "layout_bytes_per_launch": actual_b,
+                    "frac_layout": round(actual_b / (spmv_ms.value * 1e-3) / 1e9 / peak, 4)}
+        cpu_baseline = None
+        if world == 1 and not args.no_cpu:
+            cpu_baseline = cpu_baseline_leg(g, int(seeds[0]), nnz, sample_iters=args.cpu_iters)
+        line = {
+            "metric": "RWR GTEPS (nnz x iterations x seeds / s), single-seed, 20 iterations",
+            "value": round(value, 2), "unit": "GTEPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if precision == rs.FP64 else "f32", "data": "synthetic",
+            "config": {"workload": "C2: single-seed RWR, synthetic Twitter-shaped graph (1M users, 10M tweets, "
+                                   "power-law, scrambled ids), c=0.15f, 20 iterations",
+                       "n_nodes": n, "nnz": nnz, "n_links_raw": info.n_links_raw, "scale": args.scale,
+                       "seeds_per_step_per_gpu": 1, "parallelism": f"seed-sharded x{world}, graph replicated, no collective",
+                       "l2": "matrix stream per iteration (>= 0.8 GB) is larger than L2 (126 MB); no explicit flush",
+                       "hub_entries": info.hub_entries_fp64 if precision == rs.FP64 else info.hub_entries_fp32,
+                       "chunks": info.n_chunks, "max_in_degree": info.max_in_degree},
+            "gteps_iteration_loop_only": round(edges_total / (iter_ms * 1e-3) / 1e9, 2),
+            "e2e": {"value": round(e2e_value, 2), "unit": "GTEPS", "h2d_bytes_per_step": 4,
+                    "d2h_bytes_per_step": TOP_K * 16 + 4, "ms_per_step": round(e2e_ms / args.steps, 4),
+                    "seeds_per_s": round(args.steps * world / (e2e_ms * 1e-3), 2),
+                    "api": "Recommender.Recommendation(seed, 0.15f, 20, 10) -> rwr_run_fixed + rwr_topk"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu_baseline,
+            "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1),
+                      "setup_wall_s": round(setup_s, 2), "device_bytes": info.device_bytes},
+            "top1": list(last_top[0]) if last_top else None,
+        }
+    g.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(g, seed: int, nnz: int, sample_iters: int):
+    """The oracle (a port of Model.cs / Recommender.cs) on the SAME graph, collapsed O(E+N) form, one core --
+    the reference iterates one graph on one thread.  Bounded sample: `sample_iters` iterations instead of 20."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as O
+    links = g.export_links()
+    og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+    del links
+    assert og.build() == 0
+    t0 = time.perf_counter()
+    og.run(seed, O.widen_float(C_FLOAT), n_iter=sample_iters)
+    dt = time.perf_counter() - t0
+    og.close()
+    return {"value": round(nnz * sample_iters / dt / 1e9, 4), "unit": "GTEPS", "cores": 1, "kind": "port",
+            "sample": f"{sample_iters} of 20 iterations of one seed on the full graph, collapsed O(E+N) form "
+                      f"(the literal O(N^2) restart loops of Model.cs:92-93 are infeasible beyond ~10k nodes), {dt:.1f} s",
+            "host_cores": os.cpu_count()}
+
+
+# ======================================================================================================= reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path: not runnable (C#), so the oracle port, on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as O
+    spec = scaled_spec(args.scale)
+    t0 = time.perf_counter()
+    links = O.synth_generate(spec)
+    og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+    raw_deg = np.bincount(links["src"], minlength=og.n)
+    del links
+    assert og.build() == 0
+    nnz = og.nnz()
+    setup_s = time.perf_counter() - t0
+    threads = max(1, min(10, os.cpu_count() or 1))             # Semaphore(10, 10), Program.cs:11
+    sample_iters = args.cpu_iters
+    n_total = args.warmup + args.steps
+    seeds = pick_seeds(raw_deg, spec["n_users"], n_total * threads)
+    for i in range(args.warmup):
+        og.recommend_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, TOP_K, threads)
+    t0 = time.perf_counter()
+    for i in range(args.warmup, n_total):
+        og.recommend_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, TOP_K, threads)
+    dt = time.perf_counter() - t0
+    value = nnz * sample_iters * threads * args.steps / dt / 1e9
+    sample = (f"each step = {threads} seeds on {threads} threads (one graph per thread, Program.cs:11/:61-66), "
+              f"{sample_iters} of 20 iterations + top-10 each, collapsed O(E+N) form, full graph")
+    line = {
+        "impl": "reference",
+        "metric": "RWR GTEPS (nnz x iterations x seeds / s), single-seed, 20 iterations",
+        "value": round(value, 4), "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2: single-seed RWR, synthetic Twitter-shaped graph (1M users, 10M tweets, "
+                               "power-law, scrambled ids), c=0.15f, 20 iterations",
+                   "n_nodes": og.n, "nnz": nnz, "scale": args.scale},
+        "cpu_baseline": {"value": round(value, 4), "unit": "GTEPS", "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores": os.cpu_count(),
+                         "note": "the reference is C# (.NET 4.5.2); no C# toolchain in this image -> oracle port"},
+        "e2e": {"value": round(value, 4), "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "build": {"setup_wall_s": round(setup_s, 2)},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("RWR_BENCH_SCALE", "1.0")))
+    ap.add_argument("--cpu-iters", type=int, default=2, help="iterations of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

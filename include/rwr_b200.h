@@ -1,0 +1,187 @@
+/* rwr_b200.h -- C ABI of librwr_b200.so: the B200-native Random-Walk-with-Restart scoring path.
+ *
+ * Drop-in boundary for the reference's `Recommenders.RWRBased` library (C#, no FFI of its own).  Each entry
+ * point names the reference member it replaces; paths are relative to the reference repository root.
+ * The C# side keeps `Graph` / `Model` / `Recommender` signatures and forwards through P/Invoke
+ * (recommendersystems_b200/csharp/RwrNative.cs).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; the caller owns every input and output buffer, the library copies
+ *     to/from the device and never retains host pointers;
+ *   - every function returns RWR_OK (0) or a negative rwr_status; rwr_last_error() gives the message of the
+ *     last failing call on the calling thread;
+ *   - handles are opaque; functions are re-entrant across distinct handles (one CUDA stream and workspace
+ *     per graph handle); concurrent calls on the SAME handle are not supported (neither is the reference's
+ *     Model);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with RWR_E_CUDA.
+ *   - enum integer values are ABI: NodeType 0..3, EdgeType 0..7 (Recommenders/RWRBased/Recommender.cs:4-5).
+ */
+#ifndef RWR_B200_H
+#define RWR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RWR_ABI_VERSION 1
+
+typedef enum rwr_status {
+    RWR_OK = 0,
+    RWR_E_INVALID = -1,       /* bad argument (null pointer, negative size, unknown option)                    */
+    RWR_E_BADSEED = -2,       /* KeyNotFoundException at Recommender.cs:21 (seed has no `edges` entry) or a     */
+                              /* seed index outside [0, N)                                                      */
+    RWR_E_ALREADY_BUILT = -3, /* ArgumentException from Dictionary.Add when buildGraph() runs twice, Graph.cs:86 */
+    RWR_E_BADINDEX = -4,      /* IndexOutOfRangeException at Model.cs:87 (link target outside [0, N))           */
+    RWR_E_NOT_BUILT = -5,     /* KeyNotFoundException at Model.cs:79 (`graph.graph[i]` before buildGraph())      */
+    RWR_E_CUDA = -6,          /* CUDA runtime error / no device / extension not usable                          */
+    RWR_E_NCCL = -7,
+    RWR_E_OOM = -8,
+    RWR_E_UNSUPPORTED = -9
+} rwr_status;
+
+/* Recommender.cs:4 */
+enum { RWR_NODE_UNDEFINED = 0, RWR_NODE_USER = 1, RWR_NODE_ITEM = 2, RWR_NODE_ETC = 3 };
+/* Recommender.cs:5 */
+enum { RWR_EDGE_UNDEFINED = 0, RWR_EDGE_LIKE = 1, RWR_EDGE_FRIENDSHIP = 2, RWR_EDGE_FOLLOW = 3, RWR_EDGE_MENTION = 4,
+       RWR_EDGE_AUTHORSHIP = 5, RWR_EDGE_PURCHASE = 6, RWR_EDGE_ETC = 7 };
+
+enum { RWR_FP64 = 0, RWR_FP32 = 1 };
+
+/* matrix layout of the pull CSR (W^T) used by the iteration kernels */
+enum { RWR_LAYOUT_AUTO = 0,    /* index-only when every row of W has one repeated weight, else valued          */
+       RWR_LAYOUT_VALUED = 1,  /* 4 B source index + one value per link                                         */
+       RWR_LAYOUT_INDEX = 2 }; /* 4 B source index only; the row's common weight is folded into x (bit-equal)   */
+
+typedef struct rwr_graph rwr_graph;     /* ~ Recommenders.RWRBased.Graph (+ the Recommender bound to it) */
+typedef struct rwr_result rwr_result;   /* ~ Recommenders.RWRBased.Model after run(): one rank vector per seed */
+
+typedef struct rwr_opts {
+    int32_t device;        /* CUDA ordinal; -1 = current device                                                 */
+    int32_t layout;        /* RWR_LAYOUT_*                                                                      */
+    int32_t relabel;       /* 0 = auto (on): internal relabel by descending out-degree; 1 = off                 */
+    int32_t hub_entries;   /* x entries staged in shared memory per CTA; -1 = auto, 0 = none                    */
+    int32_t batch_width;   /* seed columns per SpMM tile; 0 = auto                                              */
+    int32_t reserved0;
+    uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
+} rwr_opts;
+
+/* Deterministic synthetic generator (this repository's spec; replaces TweetRecommender/DataLoader.cs:256-436
+ * and SQLiteAdapter.cs).  Integer-only, counter-based; CPU (oracle) and GPU produce identical links.        */
+typedef struct rwr_synth_spec {
+    uint64_t seed;
+    int32_t n_users, n_items, n_third;  /* node order: USER [0,U), ITEM [U,U+T), ETC [U+T,U+T+X) (DataLoader order) */
+    int32_t authorship_per_mille;       /* share of items that get an AUTHORSHIP relation                       */
+    int64_t n_like, n_friend, n_follow, n_mention;   /* relations drawn (before (src,type,dst) dedup)           */
+    int32_t undefined_per_mille;        /* share of FRIENDSHIP relations retyped UNDEFINED (Experiment.cs:84-101) */
+    int32_t scramble;                   /* 1: pseudo-random relabel so ids carry no locality                    */
+    int32_t p1_byte;                    /* per-bit probability of a 1, in 1/256 (61: R-MAT a+b = 0.76)          */
+    int32_t reserved;
+} rwr_synth_spec;
+
+typedef struct rwr_graph_info {
+    int32_t n_nodes;
+    int32_t built;
+    int64_t n_links_raw;     /* all links handed in (incl. UNDEFINED)                                           */
+    int64_t nnz;             /* explicit links == nnz(W)                                                        */
+    int32_t n_dangling;      /* rows of W without explicit links (Graph.cs:53, :86 `null`)                      */
+    int32_t layout;          /* RWR_LAYOUT_VALUED or RWR_LAYOUT_INDEX actually used                             */
+    int32_t relabelled;
+    int32_t hub_entries_fp64, hub_entries_fp32;
+    int32_t n_chunks;        /* merge-path work items of the SpMV                                               */
+    int32_t max_in_degree, max_out_degree;
+    float build_ms;          /* rwr_graph_build device time (CUDA events)                                       */
+    float synth_ms;          /* rwr_synth_create device time                                                    */
+    int64_t device_bytes;    /* device memory held by the handle                                                */
+} rwr_graph_info;
+
+typedef struct rwr_run_info {
+    int32_t n_seeds;
+    int32_t n_nodes;
+    int32_t precision;
+    int32_t iterations;      /* deliverRanks() calls of the last (or only) seed                                 */
+    double residual;         /* last L1 residual (threshold mode), else NaN                                     */
+    float iterate_ms;        /* device time of the power-iteration loop only (CUDA events on the stream)        */
+    float total_ms;          /* init + iterations (+ top-k for rwr_recommend)                                   */
+    int64_t kernel_launches; /* kernels launched by the call                                                    */
+} rwr_run_info;
+
+/* ---- library ---- */
+int rwr_abi_version(void);
+int rwr_device_count(void);                 /* number of CUDA devices, 0 if none/driver missing                  */
+const char* rwr_last_error(void);           /* thread-local, never NULL                                          */
+
+/* ---- graph: `new Graph(nodes, edges)` Graph.cs:45 ----
+ * Links are passed flattened, `for i in 0..N-1: foreach l in edges[i]`, i.e. grouped by source with each
+ * source's insertion order kept (any source order is accepted; a stable sort by source is applied when the
+ * input is not already source-ascending).  A source without links == a missing `edges` key.               */
+int rwr_graph_create(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                     const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                     const rwr_opts* opts, rwr_graph** out);
+/* generator on the device (K0); the graph is in the same "created, not built" state as after rwr_graph_create */
+int rwr_synth_create(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_graph** out);
+/* `Graph.buildGraph()` Graph.cs:51-88: out-degree count, exclusive scan, stable CSR scatter, sequential row
+ * sums, IEEE division; then the pull layout (transpose) used by the iteration.                             */
+int rwr_graph_build(rwr_graph* g);
+int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info);     /* `Graph.size()` Graph.cs:91 and more       */
+/* raw links back on the host, in the canonical (source, insertion) order (`Graph.nodes`, `Graph.edges`)    */
+int rwr_graph_export_links(rwr_graph* g, int64_t* node_id, int32_t* node_type, int32_t* src, int32_t* dst,
+                           int32_t* etype, double* w);
+/* `Graph.graph` (Graph.cs:43): row_ptr[N+1], col[nnz], val[nnz]; null rows have equal row_ptr entries      */
+int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val);
+int rwr_graph_get_degrees(rwr_graph* g, int32_t* out_degree /*N explicit links*/, int32_t* raw_degree /*N, may be NULL*/);
+void rwr_graph_destroy(rwr_graph* g);
+
+/* ---- model: `new Model(graph, c, seed)` + `run(int)` Model.cs:33-50, :68-73 ----
+ * One rank vector per seed.  seed == -1 selects the uniform-restart constructor (Model.cs:14-31).
+ * `c` is the double the reference computes with: pass (double)0.15f for `Recommendation(.., 0.15f, ..)`.    */
+int rwr_run_fixed(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int32_t n_iter,
+                  int32_t precision, rwr_result** out);
+/* `Model.run(double threshold)` Model.cs:57-66; thr <= 0 selects `Model.run()` (Model.cs:52-55:
+ * thr = (1/double.MaxValue) * N).  max_iter <= 0: unbounded like the reference (may never return when no
+ * bitwise fixed point exists); iters_out[n_seeds] receives the number of deliverRanks() calls.            */
+int rwr_run_threshold(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, double thr,
+                      int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out);
+int rwr_result_get_info(rwr_result* r, rwr_run_info* info);
+/* `Model.rank` (Model.cs:7) of one seed, widened to double in FP32 mode                                    */
+int rwr_scores(rwr_result* r, int32_t seed_slot, double* out_n);
+/* `Recommender.Recommendation(idx, c, nIter, topN)` Recommender.cs:42-51 on the ranks held by `r`:
+ * out_ids/out_scores are [n_seeds * k], out_counts[n_seeds] (fewer than k when fewer candidates).
+ * Fails with RWR_E_BADSEED when a seed has no raw links (KeyNotFoundException, Recommender.cs:21).          */
+int rwr_topk(rwr_result* r, int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts);
+/* `Recommender.Recommendation(idx, c, nIter)` Recommender.cs:14-40: the full ranking of one seed,
+ * (score desc, id desc); writes min(count, cap) pairs and the candidate count.                             */
+int rwr_rank_all(rwr_result* r, int32_t seed_slot, int64_t* ids, double* scores, int64_t cap, int64_t* count);
+void rwr_result_destroy(rwr_result* r);
+
+/* ---- fused request path: n_seeds x `Recommendation(seed, c, nIter, k)` in seed tiles (SpMM) ----
+ * Ranks are not kept; only the k best (id, score) per seed come back.                                      */
+int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int32_t n_iter,
+                  int32_t precision, int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts,
+                  rwr_run_info* info /* may be NULL */);
+
+/* ---- measurement probe: average device time of the two kernels of one iteration (CUDA events on the handle's
+ * stream, `reps` iterations after 3 warm-up iterations).  Used by bench.py for the roofline of k_spmv.      */
+int rwr_profile_iteration(rwr_graph* g, int32_t seed, double c, int32_t precision, int32_t reps, float* spmv_ms,
+                          float* fixup_ms);
+
+/* ---- evaluation (next row N1): Experiment.cs:121-128 on a ranking held on the host ---- */
+int rwr_evaluate(const int64_t* ranked_ids, int64_t n, const int64_t* test_ids, int64_t n_test, int32_t* hits,
+                 double* avg_precision);
+
+/* ---- row-partitioned single graph (no reference analogue): slices of W^T + NCCL allGather per iteration ---- */
+typedef struct rwr_comm rwr_comm;
+int rwr_comm_unique_id(void* id128 /* 128 bytes */);
+int rwr_comm_create(int32_t rank, int32_t n_ranks, const void* id128, const rwr_opts* opts, rwr_comm** out);
+void rwr_comm_destroy(rwr_comm* c);
+/* every rank generates the same graph and keeps the rows of W^T it owns (balanced by nnz)                  */
+int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_comm* comm, rwr_graph** out);
+int rwr_graph_create_partitioned(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                                 const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                                 const rwr_opts* opts, rwr_comm* comm, rwr_graph** out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RWR_B200_H */

@@ -1,0 +1,13 @@
+"""recommendersystems_b200 -- B200-native Random-Walk-with-Restart scoring path.
+
+Host-side mirror of the reference's `Recommenders.RWRBased` API (Graph / Model / Recommender, Node, ForwardLink,
+NodeType, EdgeType) on top of the C ABI of librwr_b200.so (include/rwr_b200.h).  There is no CPU fallback: the
+extension must be built (`python -c "import __graft_entry__ as g; g.build()"`) and a CUDA device must be present
+for anything that computes.
+"""
+from .rwr import (EdgeType, ForwardLink, Graph, Model, Node, NodeType, Recommender, RwrError, SynthSpec,
+                  FP32, FP64, evaluate, widen_float)
+from . import _native
+
+__all__ = ["EdgeType", "ForwardLink", "Graph", "Model", "Node", "NodeType", "Recommender", "RwrError", "SynthSpec",
+           "FP32", "FP64", "evaluate", "widen_float", "_native"]

@@ -1,0 +1,171 @@
+// common.cuh -- shared host/device helpers of librwr_b200 (sm_100a only, no fallback paths).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/rwr_b200.h"
+
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef uint8_t u8;
+
+// ------------------------------------------------------------------ error plumbing
+void rwr_set_error(const char* fmt, ...);
+
+struct RwrError {
+    int code;
+};
+
+#define RWR_FAIL(code_, ...)          \
+    do {                              \
+        rwr_set_error(__VA_ARGS__);   \
+        throw RwrError{(code_)};      \
+    } while (0)
+
+#define CUDA_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t err__ = (expr);                                                                   \
+        if (err__ != cudaSuccess) {                                                                   \
+            int code__ = (err__ == cudaErrorMemoryAllocation) ? RWR_E_OOM : RWR_E_CUDA;               \
+            rwr_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(err__), __FILE__, __LINE__); \
+            throw RwrError{code__};                                                                   \
+        }                                                                                             \
+    } while (0)
+
+#define KERNEL_CHECK() CUDA_CHECK(cudaGetLastError())
+
+// Every exported function body runs inside this guard: exceptions never cross the C ABI.
+#define RWR_API_BEGIN try {
+#define RWR_API_END                                     \
+    }                                                   \
+    catch (const RwrError& e__) { return e__.code; }    \
+    catch (const std::bad_alloc&) {                     \
+        rwr_set_error("host allocation failed");        \
+        return RWR_E_OOM;                               \
+    }                                                   \
+    catch (...) {                                       \
+        rwr_set_error("unexpected exception");          \
+        return RWR_E_INVALID;                           \
+    }
+
+// ------------------------------------------------------------------ device memory
+// Tracks bytes so rwr_graph_info.device_bytes is exact.
+struct DevPool {
+    int64_t bytes = 0;
+    int64_t launches = 0;   // kernels launched through this handle (bench "gpu_launches")
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevPool* pool = nullptr;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept { *this = std::move(o); }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; pool = o.pool;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count, DevPool* pl = nullptr) {
+        release();
+        pool = pl;
+        n = count;
+        size_t bytes = (count ? count : 1) * sizeof(T);
+        CUDA_CHECK(cudaMalloc((void**)&p, bytes));
+        if (pool) pool->bytes += (int64_t)bytes;
+    }
+    void release() {
+        if (p) {
+            cudaFree(p);
+            if (pool) pool->bytes -= (int64_t)((n ? n : 1) * sizeof(T));
+        }
+        p = nullptr;
+        n = 0;
+    }
+    operator T*() const { return p; }
+};
+
+static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+static inline int ceil_log2_u64(u64 n) {
+    int L = 0;
+    while ((1ULL << L) < n) L++;
+    return L;
+}
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// fixed-shape tree (deterministic for a given lane assignment)
+template <typename T>
+__device__ __forceinline__ T warp_sum_down(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = add_rn(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+__device__ __forceinline__ u64 policy_evict_first() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ u64 policy_evict_last() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// streamed, read-once data: bypass L1, first to leave L2
+__device__ __forceinline__ int4 ld_stream_int4(const int4* ptr, u64 pol) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(ptr), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ double ld_stream(const double* ptr, u64 pol) {
+    double r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(ptr), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_stream(const float* ptr, u64 pol) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ptr), "l"(pol));
+    return r;
+}
+// gathered, re-used data: keep in L1 and last to leave L2
+__device__ __forceinline__ double ld_keep(const double* ptr, u64 pol) {
+    double r;
+    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(ptr), "l"(pol));
+    return r;
+}
+__device__ __forceinline__ float ld_keep(const float* ptr, u64 pol) {
+    float r;
+    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ptr), "l"(pol));
+    return r;
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,629 @@
+// graph.cu -- graph handle, transition-matrix construction (K1-K5) and parity probes.
+//
+// Restates Recommenders/RWRBased/Graph.cs:51-88 (buildGraph) on the device:
+//   K1  explicit-link flags / out-degree count      Graph.cs:57-61
+//   K2  exclusive scan -> row_ptr                   (implicit in `new ForwardLink[nExplicitLinks]`, Graph.cs:66)
+//   K3  stable CSR scatter in insertion order       Graph.cs:71-77
+//   K4  sequential row sums + IEEE division         Graph.cs:70, :75, :80-81
+//   K5  pull layout: CSR of W^T (turns the push loop Model.cs:85-88 into a gather), rows and sources relabelled
+//       by descending out-degree, sources inside a row kept in the reference's accumulation order.
+#include <algorithm>
+
+#include "graph.h"
+#include "primitives.cuh"
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void k_i32_to_u8(const int32_t* __restrict__ in, u8* __restrict__ out, size_t n, int* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int32_t v = in[i];
+        if (v < 0 || v > 255) *bad = 1;
+        out[i] = (u8)v;
+    }
+}
+
+// flags[0]: a source outside [0, n); flags[1]: sources not ascending
+__global__ void k_check_src(const int32_t* __restrict__ src, size_t e0, int32_t n, int* flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e0) {
+        int32_t s = src[i];
+        if (s < 0 || s >= n) flags[0] = 1;
+        if (i > 0 && src[i - 1] > s) flags[1] = 1;
+    }
+}
+
+__global__ void k_iota(u32* out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (u32)i;
+}
+
+template <typename T>
+__global__ void k_gather(const T* __restrict__ in, const u32* __restrict__ idx, T* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[idx[i]];
+}
+
+// ptr[s] = first position p with keys[p] >= s, for s in [0, n]   (keys ascending)
+template <typename KeyT>
+__global__ void k_lower_bounds(const KeyT* __restrict__ keys, size_t e, int32_t n, u32* __restrict__ ptr) {
+    size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > (size_t)n) return;
+    size_t lo = 0, hi = e;
+    while (lo < hi) {
+        size_t mid = (lo + hi) >> 1;
+        if ((size_t)keys[mid] < s) lo = mid + 1; else hi = mid;
+    }
+    ptr[s] = (u32)lo;
+}
+
+// K1: flag explicit links (type != UNDEFINED) and validate their targets (IndexOutOfRange at Model.cs:87)
+__global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __restrict__ dst, size_t e0, int32_t n,
+                                 u32* __restrict__ flags, int* bad) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e0) {
+        u32 f = type[i] != RWR_EDGE_UNDEFINED;
+        if (f) {
+            int32_t d = dst[i];
+            if (d < 0 || d >= n) *bad = 1;
+        }
+        flags[i] = f;
+    }
+}
+
+// K3: stable compaction of the explicit links (insertion order kept: pos is an exclusive scan of the flags)
+__global__ void k_compact(const u8* __restrict__ type, const u32* __restrict__ pos, const int32_t* __restrict__ src,
+                          const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0,
+                          int32_t* __restrict__ src_of, int32_t* __restrict__ col, double* __restrict__ wv) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e0 && type[i] != RWR_EDGE_UNDEFINED) {
+        u32 p = pos[i];
+        src_of[p] = src[i];
+        col[p] = dst[i];
+        wv[p] = w[i];
+    }
+}
+
+__global__ void k_row_ptr_from_pos(const u32* __restrict__ raw_ptr, const u32* __restrict__ pos, size_t e0, u32 nnz,
+                                   int32_t n, u32* __restrict__ row_ptr) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= (size_t)n) {
+        u32 r = raw_ptr[i];
+        row_ptr[i] = (r >= e0) ? nnz : pos[r];
+    }
+}
+
+struct BuildStats {
+    int n_dangling;
+    int all_uniform;
+    u32 max_out;
+    u32 max_in;
+    int n_items;
+};
+
+// K4a: rows with <= 32 links, one thread per row, strictly sequential sum (Graph.cs:70-77 order)
+// K4b: longer rows, one warp per row: all-ones rows sum exactly to their length, anything else is summed
+//      sequentially by lane 0 to keep the reference's rounding.
+constexpr u32 ROWSUM_SHORT = 32;
+
+__device__ __forceinline__ void rowsum_finish(int32_t i, u32 deg, double sum, double w0, bool uniform, double* rowsum,
+                                              double* w0norm, u8* uni, BuildStats* st) {
+    rowsum[i] = sum;
+    w0norm[i] = deg ? __ddiv_rn(w0, sum) : 0.0;
+    uni[i] = uniform ? 1 : 0;
+    if (deg == 0) atomicAdd(&st->n_dangling, 1);
+    else if (!uniform) atomicAnd(&st->all_uniform, 0);
+    atomicMax(&st->max_out, deg);
+}
+
+__global__ void k_rowsum_short(const u32* __restrict__ row_ptr, const double* __restrict__ wv, int32_t n,
+                               double* __restrict__ rowsum, double* __restrict__ w0norm, u8* __restrict__ uni,
+                               BuildStats* st) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    u32 b = row_ptr[i], e = row_ptr[i + 1], deg = e - b;
+    if (deg > ROWSUM_SHORT) return;
+    double sum = 0.0, w0 = deg ? wv[b] : 0.0;
+    bool uniform = true;
+    for (u32 k = b; k < e; k++) {
+        double w = wv[k];
+        sum = __dadd_rn(sum, w);
+        uniform = uniform && (w == w0);
+    }
+    rowsum_finish(i, deg, sum, w0, uniform, rowsum, w0norm, uni, st);
+}
+
+__global__ void k_rowsum_long(const u32* __restrict__ row_ptr, const double* __restrict__ wv, int32_t n,
+                              double* __restrict__ rowsum, double* __restrict__ w0norm, u8* __restrict__ uni,
+                              BuildStats* st) {
+    int32_t i = (int32_t)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    int lane = threadIdx.x & 31;
+    if (i >= n) return;
+    u32 b = row_ptr[i], e = row_ptr[i + 1], deg = e - b;
+    if (deg <= ROWSUM_SHORT) return;
+    double w0 = wv[b];
+    bool same = true;
+    for (u32 k = b + lane; k < e; k += 32) same = same && (wv[k] == w0);
+    bool uniform = __all_sync(0xffffffffu, same);
+    if (lane == 0) {
+        double sum;
+        if (uniform && w0 == 1.0) {
+            sum = (double)deg;                       // deg sequential additions of 1.0 are exact
+        } else {
+            sum = 0.0;
+            for (u32 k = b; k < e; k++) sum = __dadd_rn(sum, wv[k]);
+        }
+        rowsum_finish(i, deg, sum, w0, uniform, rowsum, w0norm, uni, st);
+    }
+}
+
+// K4c: Graph.cs:80-81
+__global__ void k_normalise(const double* __restrict__ wv, const int32_t* __restrict__ src_of,
+                            const double* __restrict__ rowsum, size_t nnz, double* __restrict__ val) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) val[i] = __ddiv_rn(wv[i], rowsum[src_of[i]]);
+}
+
+__global__ void k_degree_keys(const u32* __restrict__ row_ptr, int32_t n, u32 max_out, u32* __restrict__ keys,
+                              u32* __restrict__ vals) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        keys[i] = max_out - (row_ptr[i + 1] - row_ptr[i]);
+        vals[i] = (u32)i;
+    }
+}
+
+__global__ void k_invert_perm(const u32* __restrict__ old_of_new_u, int32_t n, int32_t* __restrict__ old_of_new,
+                              int32_t* __restrict__ new_of_old) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) {
+        int32_t o = (int32_t)old_of_new_u[j];
+        old_of_new[j] = o;
+        new_of_old[o] = j;
+    }
+}
+
+__global__ void k_identity_perm(int32_t n, int32_t* a, int32_t* b) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { a[j] = j; b[j] = j; }
+}
+
+__global__ void k_transpose_keys(const int32_t* __restrict__ col, const int32_t* __restrict__ new_of_old, size_t nnz,
+                                 u32* __restrict__ keys, u32* __restrict__ vals) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nnz) {
+        keys[i] = (u32)new_of_old[col[i]];
+        vals[i] = (u32)i;
+    }
+}
+
+__global__ void k_fill_pull(const u32* __restrict__ order, const int32_t* __restrict__ src_of,
+                            const int32_t* __restrict__ new_of_old, const double* __restrict__ val, size_t nnz,
+                            int32_t* __restrict__ in_src, double* __restrict__ in_val /* may be null */) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < nnz) {
+        u32 e = order[p];
+        in_src[p] = new_of_old[src_of[e]];
+        if (in_val) in_val[p] = val[e];
+    }
+}
+
+__global__ void k_node_arrays(const int32_t* __restrict__ old_of_new, const u32* __restrict__ row_ptr,
+                              const double* __restrict__ w0norm, const u8* __restrict__ uni,
+                              const int64_t* __restrict__ node_id, const u8* __restrict__ node_type, int32_t n,
+                              int index_layout, const u32* __restrict__ in_ptr, double* __restrict__ inv_orig,
+                              double* __restrict__ inv_int, int64_t* __restrict__ id_int, u8* __restrict__ type_int,
+                              BuildStats* st) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    int32_t o = old_of_new[j];
+    u32 deg = row_ptr[o + 1] - row_ptr[o];
+    double inv = (deg == 0) ? 0.0 : (index_layout ? w0norm[o] : 1.0);
+    (void)uni;
+    inv_orig[o] = inv;
+    inv_int[j] = inv;
+    id_int[j] = node_id[o];
+    u8 t = node_type[o];
+    type_int[j] = t;
+    if (t == RWR_NODE_ITEM) atomicAdd(&st->n_items, 1);
+    atomicMax(&st->max_in, in_ptr[j + 1] - in_ptr[j]);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static inline unsigned grid_for(size_t n, int block = 256) { return n ? div_up(n, block) : 1; }
+
+void graph_init_device(rwr_graph* g, const rwr_opts* opts) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        RWR_FAIL(RWR_E_CUDA, "no CUDA device: librwr_b200 has no CPU fallback");
+    if (opts) g->opts = *opts; else { memset(&g->opts, 0, sizeof(g->opts)); g->opts.device = -1; g->opts.hub_entries = -1; }
+    if (g->opts.device >= 0) {
+        if (g->opts.device >= ndev) RWR_FAIL(RWR_E_INVALID, "device %d out of range (%d devices)", g->opts.device, ndev);
+        CUDA_CHECK(cudaSetDevice(g->opts.device));
+    }
+    CUDA_CHECK(cudaGetDevice(&g->device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, g->device));
+    if (prop.major < 10)
+        RWR_FAIL(RWR_E_CUDA, "device %d is sm_%d%d; librwr_b200 is built for sm_100a only", g->device, prop.major, prop.minor);
+    g->sm_count = prop.multiProcessorCount;
+    g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (g->opts.stream) {
+        g->stream = (cudaStream_t)(uintptr_t)g->opts.stream;
+        g->own_stream = false;
+    } else {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+        g->own_stream = true;
+    }
+}
+
+// Canonicalise the raw links: stable sort by source when needed, then raw_ptr.
+void graph_finish_create(rwr_graph* g) {
+    cudaStream_t st = g->stream;
+    const size_t e0 = (size_t)g->e0;
+    DevBuf<int> flags;
+    flags.alloc(2);
+    CUDA_CHECK(cudaMemsetAsync(flags.p, 0, 2 * sizeof(int), st));
+    if (e0) {
+        k_check_src<<<grid_for(e0), 256, 0, st>>>(g->raw_src.p, e0, g->n, flags.p);
+        KERNEL_CHECK();
+    }
+    int h[2];
+    CUDA_CHECK(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h[0]) RWR_FAIL(RWR_E_BADINDEX, "link source outside [0, %d)", g->n);
+    if (h[1]) {
+        // not source-ascending: stable sort by source keeps each source's insertion order
+        DevBuf<u32> keys, keys_alt, ord, ord_alt;
+        keys.alloc(e0); keys_alt.alloc(e0); ord.alloc(e0); ord_alt.alloc(e0);
+        CUDA_CHECK(cudaMemcpyAsync(keys.p, g->raw_src.p, e0 * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        k_iota<<<grid_for(e0), 256, 0, st>>>(ord.p, e0);
+        KERNEL_CHECK();
+        bool fl = prim::radix_sort<u32>(keys.p, keys_alt.p, ord.p, ord_alt.p, e0, ceil_log2_u64((u64)g->n), st, &g->pool);
+        u32* order = fl ? ord_alt.p : ord.p;
+        u32* sorted = fl ? keys_alt.p : keys.p;
+        DevBuf<int32_t> dst2; DevBuf<u8> type2; DevBuf<double> w2;
+        dst2.alloc(e0, &g->pool); type2.alloc(e0, &g->pool); w2.alloc(e0, &g->pool);
+        k_gather<int32_t><<<grid_for(e0), 256, 0, st>>>(g->raw_dst.p, order, dst2.p, e0);
+        k_gather<u8><<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, order, type2.p, e0);
+        k_gather<double><<<grid_for(e0), 256, 0, st>>>(g->raw_w.p, order, w2.p, e0);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(g->raw_src.p, sorted, e0 * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        g->raw_dst = std::move(dst2);
+        g->raw_type = std::move(type2);
+        g->raw_w = std::move(w2);
+    }
+    g->raw_ptr.alloc((size_t)g->n + 1, &g->pool);
+    k_lower_bounds<int32_t><<<grid_for((size_t)g->n + 1), 256, 0, st>>>(g->raw_src.p, e0, g->n, g->raw_ptr.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+static void graph_build_impl(rwr_graph* g) {
+    if (g->built) RWR_FAIL(RWR_E_ALREADY_BUILT, "buildGraph() called twice (ArgumentException at Graph.cs:86)");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    const size_t e0 = (size_t)g->e0;
+    const int32_t n = g->n;
+    cudaEvent_t ev0, ev1;
+    CUDA_CHECK(cudaEventCreate(&ev0));
+    CUDA_CHECK(cudaEventCreate(&ev1));
+    CUDA_CHECK(cudaEventRecord(ev0, st));
+
+    DevBuf<BuildStats> stats;
+    stats.alloc(1);
+    BuildStats hs = {0, 1, 0, 0, 0};
+    CUDA_CHECK(cudaMemcpyAsync(stats.p, &hs, sizeof(hs), cudaMemcpyHostToDevice, st));
+    DevBuf<int> bad;
+    bad.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+
+    // ---- K1 + K2: explicit flags, exclusive scan
+    DevBuf<u32> pos, total;
+    pos.alloc(e0);
+    total.alloc(1);
+    if (e0) {
+        k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, n, pos.p, bad.p);
+        KERNEL_CHECK();
+    }
+    prim::exclusive_scan<u32>(pos.p, pos.p, e0, total.p, st, &g->pool);
+    u32 h_total = 0;
+    int h_bad = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_total, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_bad) RWR_FAIL(RWR_E_BADINDEX, "link target outside [0, %d) (IndexOutOfRangeException at Model.cs:87)", n);
+    const size_t nnz = h_total;
+    g->nnz = (int64_t)nnz;
+
+    // ---- K3: stable scatter (skipped when no UNDEFINED link exists: the raw arrays already are the CSR)
+    DevBuf<double> wv_own;
+    const double* wv;
+    if (nnz == e0) {
+        g->compacted = false;
+        g->row_ptr = g->raw_ptr.p;
+        g->col = g->raw_dst.p;
+        g->src_of = g->raw_src.p;
+        wv = g->raw_w.p;
+    } else {
+        g->compacted = true;
+        g->row_ptr_own.alloc((size_t)n + 1, &g->pool);
+        g->col_own.alloc(nnz, &g->pool);
+        g->src_of_own.alloc(nnz, &g->pool);
+        wv_own.alloc(nnz);
+        k_compact<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, g->raw_src.p, g->raw_dst.p, g->raw_w.p, e0,
+                                                g->src_of_own.p, g->col_own.p, wv_own.p);
+        k_row_ptr_from_pos<<<grid_for((size_t)n + 1), 256, 0, st>>>(g->raw_ptr.p, pos.p, e0, (u32)nnz, n, g->row_ptr_own.p);
+        KERNEL_CHECK();
+        g->row_ptr = g->row_ptr_own.p;
+        g->col = g->col_own.p;
+        g->src_of = g->src_of_own.p;
+        wv = wv_own.p;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    pos.release();
+
+    // ---- K4: row sums (sequential order), normalisation
+    DevBuf<double> rowsum, w0norm;
+    DevBuf<u8> uni;
+    rowsum.alloc(n); w0norm.alloc(n); uni.alloc(n);
+    if (n) {
+        k_rowsum_short<<<grid_for(n), 256, 0, st>>>(g->row_ptr, wv, n, rowsum.p, w0norm.p, uni.p, stats.p);
+        k_rowsum_long<<<grid_for((size_t)n * 32), 256, 0, st>>>(g->row_ptr, wv, n, rowsum.p, w0norm.p, uni.p, stats.p);
+        KERNEL_CHECK();
+    }
+    g->val.alloc(nnz, &g->pool);
+    if (nnz) {
+        k_normalise<<<grid_for(nnz), 256, 0, st>>>(wv, g->src_of, rowsum.p, nnz, g->val.p);
+        KERNEL_CHECK();
+    }
+    CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    wv_own.release();
+    g->n_dangling = hs.n_dangling;
+    g->all_uniform = hs.all_uniform != 0;
+    g->max_out_degree = hs.max_out;
+
+    int layout = g->opts.layout;
+    if (layout == RWR_LAYOUT_AUTO) layout = g->all_uniform ? RWR_LAYOUT_INDEX : RWR_LAYOUT_VALUED;
+    if (layout == RWR_LAYOUT_INDEX && !g->all_uniform)
+        RWR_FAIL(RWR_E_UNSUPPORTED, "index-only layout needs one repeated weight per row of W (found non-uniform rows)");
+    if (layout != RWR_LAYOUT_INDEX && layout != RWR_LAYOUT_VALUED) RWR_FAIL(RWR_E_INVALID, "unknown layout %d", layout);
+    g->layout = layout;
+
+    // ---- internal relabel by descending out-degree (== how often x_i is gathered)
+    g->new_of_old.alloc(n, &g->pool);
+    g->old_of_new.alloc(n, &g->pool);
+    g->relabelled = (g->opts.relabel == 0) && n > 1;
+    if (g->relabelled) {
+        DevBuf<u32> k0, k1, v0, v1;
+        k0.alloc(n); k1.alloc(n); v0.alloc(n); v1.alloc(n);
+        k_degree_keys<<<grid_for(n), 256, 0, st>>>(g->row_ptr, n, hs.max_out, k0.p, v0.p);
+        KERNEL_CHECK();
+        bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, n, ceil_log2_u64((u64)hs.max_out + 1), st, &g->pool);
+        k_invert_perm<<<grid_for(n), 256, 0, st>>>(fl ? v1.p : v0.p, n, g->old_of_new.p, g->new_of_old.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    } else if (n) {
+        k_identity_perm<<<grid_for(n), 256, 0, st>>>(n, g->old_of_new.p, g->new_of_old.p);
+        KERNEL_CHECK();
+    }
+
+    // ---- K5: transpose to the pull layout with a stable sort keyed by the (relabelled) target
+    g->in_ptr.alloc((size_t)n + 1, &g->pool);
+    g->in_src.alloc(nnz + IDX_PAD, &g->pool);
+    CUDA_CHECK(cudaMemsetAsync(g->in_src.p, 0, (nnz + IDX_PAD) * sizeof(int32_t), st));
+    if (layout == RWR_LAYOUT_VALUED) g->in_val64.alloc(nnz, &g->pool);
+    {
+        DevBuf<u32> k0, k1, v0, v1;
+        k0.alloc(nnz); k1.alloc(nnz); v0.alloc(nnz); v1.alloc(nnz);
+        if (nnz) {
+            k_transpose_keys<<<grid_for(nnz), 256, 0, st>>>(g->col, g->new_of_old.p, nnz, k0.p, v0.p);
+            KERNEL_CHECK();
+        }
+        bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, nnz, ceil_log2_u64((u64)n), st, &g->pool);
+        const u32* sorted = fl ? k1.p : k0.p;
+        const u32* order = fl ? v1.p : v0.p;
+        k_lower_bounds<u32><<<grid_for((size_t)n + 1), 256, 0, st>>>(sorted, nnz, n, g->in_ptr.p);
+        if (nnz)
+            k_fill_pull<<<grid_for(nnz), 256, 0, st>>>(order, g->src_of, g->new_of_old.p, g->val.p, nnz, g->in_src.p,
+                                                      layout == RWR_LAYOUT_VALUED ? g->in_val64.p : nullptr);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+
+    // ---- per-node arrays in internal labels
+    g->inv_orig.alloc(n, &g->pool);
+    g->inv64.alloc(n, &g->pool);
+    g->node_id_int.alloc(n, &g->pool);
+    g->node_type_int.alloc(n, &g->pool);
+    if (n) {
+        k_node_arrays<<<grid_for(n), 256, 0, st>>>(g->old_of_new.p, g->row_ptr, w0norm.p, uni.p, g->node_id.p,
+                                                   g->node_type.p, n, layout == RWR_LAYOUT_INDEX, g->in_ptr.p,
+                                                   g->inv_orig.p, g->inv64.p, g->node_id_int.p, g->node_type_int.p, stats.p);
+        KERNEL_CHECK();
+    }
+    CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g->max_in_degree = hs.max_in;
+    g->n_items = hs.n_items;
+
+    iterate_prepare(g);
+
+    CUDA_CHECK(cudaEventRecord(ev1, st));
+    CUDA_CHECK(cudaEventSynchronize(ev1));
+    CUDA_CHECK(cudaEventElapsedTime(&g->build_ms, ev0, ev1));
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+    g->built = true;
+}
+
+// ------------------------------------------------------------------------------------------------ C ABI
+extern "C" {
+
+int rwr_graph_create(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                     const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                     const rwr_opts* opts, rwr_graph** out) {
+    rwr_graph* g = nullptr;
+    RWR_API_BEGIN
+    if (!out) RWR_FAIL(RWR_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (n_nodes < 0 || n_links < 0) RWR_FAIL(RWR_E_INVALID, "negative size");
+    if ((n_nodes && (!node_id || !node_type)) || (n_links && (!src || !dst || !etype || !w)))
+        RWR_FAIL(RWR_E_INVALID, "NULL input array");
+    if ((u64)n_nodes >= (1ULL << 28)) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^28-1 nodes");
+    if ((u64)n_links >= (1ULL << 32) - 65536) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 links per device");
+    g = new rwr_graph();
+    graph_init_device(g, opts);
+    cudaStream_t st = g->stream;
+    g->n = n_nodes;
+    g->e0 = n_links;
+    const size_t n = (size_t)n_nodes, e0 = (size_t)n_links;
+    g->node_id.alloc(n, &g->pool);
+    g->node_type.alloc(n, &g->pool);
+    g->raw_src.alloc(e0, &g->pool);
+    g->raw_dst.alloc(e0, &g->pool);
+    g->raw_type.alloc(e0, &g->pool);
+    g->raw_w.alloc(e0, &g->pool);
+    DevBuf<int32_t> tmp;
+    tmp.alloc(std::max(n, e0));
+    DevBuf<int> bad;
+    bad.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(g->node_id.p, node_id, n * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(tmp.p, node_type, n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        k_i32_to_u8<<<grid_for(n), 256, 0, st>>>(tmp.p, g->node_type.p, n, bad.p);
+        KERNEL_CHECK();
+    }
+    if (e0) {
+        CUDA_CHECK(cudaMemcpyAsync(g->raw_src.p, src, e0 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(g->raw_dst.p, dst, e0 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(g->raw_w.p, w, e0 * sizeof(double), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));   // tmp is reused
+        CUDA_CHECK(cudaMemcpyAsync(tmp.p, etype, e0 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        k_i32_to_u8<<<grid_for(e0), 256, 0, st>>>(tmp.p, g->raw_type.p, e0, bad.p);
+        KERNEL_CHECK();
+    }
+    int h_bad = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h_bad) RWR_FAIL(RWR_E_INVALID, "node_type / etype value outside 0..255");
+    graph_finish_create(g);
+    *out = g;
+    return RWR_OK;
+    }
+    catch (const RwrError& e__) { rwr_graph_destroy(g); return e__.code; }
+    catch (...) { rwr_graph_destroy(g); rwr_set_error("unexpected exception"); return RWR_E_INVALID; }
+}
+
+int rwr_graph_build(rwr_graph* g) {
+    RWR_API_BEGIN
+    if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
+    graph_build_impl(g);
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info) {
+    RWR_API_BEGIN
+    if (!g || !info) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    memset(info, 0, sizeof(*info));
+    info->n_nodes = g->n;
+    info->built = g->built ? 1 : 0;
+    info->n_links_raw = g->e0;
+    info->nnz = g->built ? g->nnz : 0;
+    info->n_dangling = g->n_dangling;
+    info->layout = g->built ? g->layout : 0;
+    info->relabelled = g->relabelled ? 1 : 0;
+    info->hub_entries_fp64 = g->built ? hub_entries_for(g, RWR_FP64) : 0;
+    info->hub_entries_fp32 = g->built ? hub_entries_for(g, RWR_FP32) : 0;
+    info->n_chunks = g->n_chunks;
+    info->max_in_degree = (int32_t)g->max_in_degree;
+    info->max_out_degree = (int32_t)g->max_out_degree;
+    info->build_ms = g->build_ms;
+    info->synth_ms = g->synth_ms;
+    info->device_bytes = g->pool.bytes;
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_graph_export_links(rwr_graph* g, int64_t* node_id, int32_t* node_type, int32_t* src, int32_t* dst,
+                           int32_t* etype, double* w) {
+    RWR_API_BEGIN
+    if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    const size_t n = (size_t)g->n, e0 = (size_t)g->e0;
+    if (node_id && n) CUDA_CHECK(cudaMemcpyAsync(node_id, g->node_id.p, n * 8, cudaMemcpyDeviceToHost, st));
+    if (src && e0) CUDA_CHECK(cudaMemcpyAsync(src, g->raw_src.p, e0 * 4, cudaMemcpyDeviceToHost, st));
+    if (dst && e0) CUDA_CHECK(cudaMemcpyAsync(dst, g->raw_dst.p, e0 * 4, cudaMemcpyDeviceToHost, st));
+    if (w && e0) CUDA_CHECK(cudaMemcpyAsync(w, g->raw_w.p, e0 * 8, cudaMemcpyDeviceToHost, st));
+    std::vector<u8> t8;
+    if (node_type && n) {
+        t8.resize(n);
+        CUDA_CHECK(cudaMemcpyAsync(t8.data(), g->node_type.p, n, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < n; i++) node_type[i] = t8[i];
+    }
+    if (etype && e0) {
+        t8.resize(e0);
+        CUDA_CHECK(cudaMemcpyAsync(t8.data(), g->raw_type.p, e0, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i < e0; i++) etype[i] = t8[i];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val) {
+    RWR_API_BEGIN
+    if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
+    if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    const size_t n = (size_t)g->n, nnz = (size_t)g->nnz;
+    if (col && nnz) CUDA_CHECK(cudaMemcpyAsync(col, g->col, nnz * 4, cudaMemcpyDeviceToHost, st));
+    if (val && nnz) CUDA_CHECK(cudaMemcpyAsync(val, g->val.p, nnz * 8, cudaMemcpyDeviceToHost, st));
+    if (row_ptr) {
+        std::vector<u32> rp(n + 1);
+        CUDA_CHECK(cudaMemcpyAsync(rp.data(), g->row_ptr, (n + 1) * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        for (size_t i = 0; i <= n; i++) row_ptr[i] = (int64_t)rp[i];
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_graph_get_degrees(rwr_graph* g, int32_t* out_degree, int32_t* raw_degree) {
+    RWR_API_BEGIN
+    if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    const size_t n = (size_t)g->n;
+    std::vector<u32> rp(n + 1);
+    if (out_degree) {
+        if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+        CUDA_CHECK(cudaMemcpyAsync(rp.data(), g->row_ptr, (n + 1) * 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        for (size_t i = 0; i < n; i++) out_degree[i] = (int32_t)(rp[i + 1] - rp[i]);
+    }
+    if (raw_degree) {
+        CUDA_CHECK(cudaMemcpyAsync(rp.data(), g->raw_ptr.p, (n + 1) * 4, cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        for (size_t i = 0; i < n; i++) raw_degree[i] = (int32_t)(rp[i + 1] - rp[i]);
+    }
+    return RWR_OK;
+    RWR_API_END
+}
+
+void rwr_graph_destroy(rwr_graph* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+}  // extern "C"

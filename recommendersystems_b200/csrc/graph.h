@@ -1,0 +1,82 @@
+// graph.h -- the device-resident graph handle shared by the translation units of librwr_b200.
+#pragma once
+
+#include "common.cuh"
+
+// Merge-path work item geometry of the SpMV (iterate.cu).  One chunk = CHUNK_ITEMS path items (rows + nnz),
+// so a chunk holds at most CHUNK_ITEMS non-zeros; with the <= 3 alignment slack of the int4 index loads its
+// span fits the CHUNK_SPAN-entry product buffer.
+constexpr int GROUP_THREADS = 256;
+constexpr int CHUNK_ROUNDS = 2;                                   // int4 index loads per thread per chunk
+constexpr int CHUNK_SPAN = GROUP_THREADS * 4 * CHUNK_ROUNDS;      // 2048
+constexpr int CHUNK_ITEMS = CHUNK_SPAN - 4;                       // 2044
+constexpr int IDX_PAD = 8;                                        // ints of slack after the index array
+
+struct rwr_comm;
+
+struct rwr_graph {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    rwr_opts opts{};
+    DevPool pool;
+
+    int32_t n = 0;          // nodes
+    int64_t e0 = 0;         // raw links
+    bool built = false;
+
+    // ---- Graph.nodes / Graph.edges (original labels, canonical (source, insertion) order)
+    DevBuf<int64_t> node_id;
+    DevBuf<u8> node_type;
+    DevBuf<int32_t> raw_src, raw_dst;
+    DevBuf<u8> raw_type;
+    DevBuf<double> raw_w;
+    DevBuf<u32> raw_ptr;    // [n+1]
+
+    // ---- Graph.graph: push CSR of W in original labels (parity probe A1-A3)
+    int64_t nnz = 0;
+    bool compacted = false;             // false: col/src_of alias raw_dst/raw_src, row_ptr aliases raw_ptr
+    DevBuf<u32> row_ptr_own;
+    DevBuf<int32_t> col_own, src_of_own;
+    DevBuf<double> val;                 // normalised weights [nnz]
+    u32* row_ptr = nullptr;             // [n+1]
+    int32_t* col = nullptr;             // [nnz]
+    int32_t* src_of = nullptr;          // [nnz] source of every explicit link
+    DevBuf<double> inv_orig;            // [n] original labels: common normalised weight of a uniform row, 1.0 for a
+                                        //     non-uniform row, 0.0 for a dangling row
+    int32_t n_dangling = 0;
+    bool all_uniform = false;
+    u32 max_out_degree = 0, max_in_degree = 0;
+
+    // ---- internal labelling (descending out-degree) and the pull CSR of W^T in internal labels
+    bool relabelled = false;
+    DevBuf<int32_t> new_of_old, old_of_new;   // [n]
+    int layout = RWR_LAYOUT_VALUED;
+    DevBuf<u32> in_ptr;                 // [n+1]
+    DevBuf<int32_t> in_src;             // [nnz + IDX_PAD] internal source ids, original-source ascending inside a row
+    DevBuf<double> in_val64;            // [nnz] (valued layout)
+    DevBuf<float> in_val32;             // lazily built for FP32 runs
+    DevBuf<double> inv64;               // [n] internal labels
+    DevBuf<float> inv32;
+    DevBuf<int2> part;                  // [n_chunks + 1] merge-path start coordinates (row, nnz)
+    int32_t n_chunks = 0;
+    DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
+    DevBuf<u8> node_type_int;
+    DevBuf<int32_t> items_by_id_desc;   // lazily: internal indices of ITEM nodes, id descending (full ranking)
+    int32_t n_items = 0;
+
+    // ---- row-partitioned mode
+    rwr_comm* comm = nullptr;
+    int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
+
+    float build_ms = 0.f, synth_ms = 0.f;
+    int sm_count = 148;
+    int max_smem_optin = 0;
+};
+
+// graph.cu
+void graph_init_device(rwr_graph* g, const rwr_opts* opts);
+void graph_finish_create(rwr_graph* g);          // canonicalise raw links on the device (sort by source if needed)
+// iterate.cu
+void iterate_prepare(rwr_graph* g);              // partition table, hub sizing
+int hub_entries_for(const rwr_graph* g, int precision);

@@ -1,0 +1,30 @@
+// iterate.h -- run state shared by iterate.cu (power iteration) and select.cu (top-k / ranking).
+#pragma once
+
+#include "graph.h"
+
+struct IterCtl {
+    double S;          // restart mass of the iteration being computed: sum_{non-dangling}(r - fl((1-c) r)) + sum_{dangling} r
+    double resid;      // last L1 residual sum |r - y|  (Model.cs:110-115)
+    double seed_sum;   // pull sum of the seed row, parked by the SpMV for the fix-up kernel
+    int seed_flag;
+    int done;          // threshold mode: converged, later launches are no-ops
+    int iters;         // deliverRanks() calls performed
+    unsigned ticket;
+};
+
+struct rwr_result {
+    rwr_graph* g = nullptr;            // the caller keeps the graph alive while results exist
+    int device = 0;
+    int32_t n_seeds = 0;
+    int32_t precision = RWR_FP64;
+    std::vector<int32_t> seeds;        // original labels (-1: uniform restart)
+    std::vector<int32_t> iters;
+    double residual = 0.0;
+    float iterate_ms = 0.f, total_ms = 0.f;
+    int64_t launches = 0;
+    // ranks, internal labels: column s occupies [s*ld, s*ld + n)
+    size_t ld = 0;
+    DevBuf<double> y64;
+    DevBuf<float> y32;
+};

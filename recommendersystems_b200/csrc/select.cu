@@ -1,0 +1,400 @@
+// select.cu -- per-seed candidate filtering, top-k (K9) and full ranking.
+//
+// Restates Recommenders/RWRBased/Recommender.cs:
+//   :19-24  exclusion list = targets of the seed's raw LIKE links            -> k_mark_excluded (bitmap)
+//   :27-31  candidates = ITEM nodes not excluded, as (node.id, rank[i])       -> filter inside the scan
+//   :34-38  order by score descending, ties by id descending                 -> 64-bit order-preserving score key, id
+//   :42-51  first topN of that order                                         -> k_topk_scan + k_topk_merge (k <= 16)
+//   :14-40  the full ranking (what Experiment.cs:121-128 walks)               -> stable LSD radix sort over items that
+//                                                                               are pre-ordered by id descending
+#include <algorithm>
+#include <unordered_set>
+
+#include "iterate.h"
+#include "primitives.cuh"
+
+constexpr int TOPK_MAX = 16;
+constexpr int TOPK_THREADS = 256;
+
+struct Cand {
+    u64 key;       // order-preserving image of the score (NaN lowest, like System.Double.CompareTo)
+    int64_t id;
+    int idx;       // internal node index, -1: empty
+};
+
+__device__ __forceinline__ u64 score_key(double s) {
+    if (s != s) return 0ULL;                         // NaN sorts below everything
+    if (s == 0.0) s = 0.0;                           // -0.0 == +0.0 for CompareTo
+    const u64 b = (u64)__double_as_longlong(s);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+}
+
+__device__ __forceinline__ bool better(const Cand& a, const Cand& b) {   // a ranks before b
+    if (a.idx < 0) return false;
+    if (b.idx < 0) return true;
+    if (a.key != b.key) return a.key > b.key;
+    return a.id > b.id;
+}
+
+__device__ __forceinline__ void list_insert(Cand (&list)[TOPK_MAX], const Cand& c) {
+    if (!better(c, list[TOPK_MAX - 1])) return;
+    list[TOPK_MAX - 1] = c;
+#pragma unroll
+    for (int i = TOPK_MAX - 1; i > 0; i--) {
+        if (better(list[i], list[i - 1])) {
+            Cand t = list[i]; list[i] = list[i - 1]; list[i - 1] = t;
+        }
+    }
+}
+
+__device__ __forceinline__ Cand cand_shfl_down(const Cand& c, int o) {
+    Cand r;
+    r.key = __shfl_down_sync(0xffffffffu, c.key, o);
+    r.id = __shfl_down_sync(0xffffffffu, c.id, o);
+    r.idx = __shfl_down_sync(0xffffffffu, c.idx, o);
+    return r;
+}
+
+// k rounds of block-wide arg-best over the heads of the per-thread sorted lists; winners go to out[0..k)
+__device__ void block_extract(Cand (&list)[TOPK_MAX], int k, Cand* out, Cand* sm_best /*[warps]*/, int* sm_owner /*[warps+1]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int round = 0; round < k; round++) {
+        Cand best = list[0];
+        int owner = threadIdx.x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            Cand other = cand_shfl_down(best, o);
+            int oo = __shfl_down_sync(0xffffffffu, owner, o);
+            if (better(other, best)) { best = other; owner = oo; }
+        }
+        if (lane == 0) { sm_best[warp] = best; sm_owner[warp] = owner; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            Cand b = sm_best[0];
+            int ow = sm_owner[0];
+            for (int w = 1; w < TOPK_THREADS / 32; w++)
+                if (better(sm_best[w], b)) { b = sm_best[w]; ow = sm_owner[w]; }
+            out[round] = b;
+            sm_owner[TOPK_THREADS / 32] = (b.idx < 0) ? -1 : ow;
+        }
+        __syncthreads();
+        const int win = sm_owner[TOPK_THREADS / 32];
+        if (win == (int)threadIdx.x) {
+#pragma unroll
+            for (int i = 0; i < TOPK_MAX - 1; i++) list[i] = list[i + 1];
+            list[TOPK_MAX - 1].idx = -1;
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict__ y, const u8* __restrict__ type_int,
+                                                            const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
+                                                            int n, int k, Cand* __restrict__ block_out) {
+    __shared__ Cand sm_best[TOPK_THREADS / 32];
+    __shared__ int sm_owner[TOPK_THREADS / 32 + 1];
+    Cand list[TOPK_MAX];
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; i++) { list[i].key = 0; list[i].id = 0; list[i].idx = -1; }
+    for (int j = blockIdx.x * TOPK_THREADS + threadIdx.x; j < n; j += gridDim.x * TOPK_THREADS) {
+        if (type_int[j] != RWR_NODE_ITEM) continue;
+        if ((excl[j >> 5] >> (j & 31)) & 1u) continue;
+        Cand c;
+        c.key = score_key((double)y[j]);
+        c.idx = j;
+        const Cand& worst = list[TOPK_MAX - 1];
+        if (worst.idx >= 0 && c.key < worst.key) continue;       // cheap reject before touching the id
+        c.id = id_int[j];
+        list_insert(list, c);
+    }
+    block_extract(list, k, block_out + (size_t)blockIdx.x * k, sm_best, sm_owner);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_merge(const Cand* __restrict__ cands, int n_cands, int k,
+                                                             const T* __restrict__ y, int64_t* __restrict__ out_ids,
+                                                             double* __restrict__ out_scores, int* __restrict__ out_count) {
+    __shared__ Cand sm_best[TOPK_THREADS / 32];
+    __shared__ int sm_owner[TOPK_THREADS / 32 + 1];
+    __shared__ Cand result[TOPK_MAX];
+    Cand list[TOPK_MAX];
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; i++) { list[i].key = 0; list[i].id = 0; list[i].idx = -1; }
+    for (int j = threadIdx.x; j < n_cands; j += TOPK_THREADS) {
+        Cand c = cands[j];
+        if (c.idx >= 0) list_insert(list, c);
+    }
+    block_extract(list, k, result, sm_best, sm_owner);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int cnt = 0;
+        for (int i = 0; i < k; i++) {
+            if (result[i].idx < 0) break;
+            out_ids[i] = result[i].id;
+            out_scores[i] = (double)y[result[i].idx];
+            cnt++;
+        }
+        *out_count = cnt;
+    }
+}
+
+// Recommender.cs:20-24 -- targets of the seed's RAW links of type LIKE (original labels -> internal bitmap)
+__global__ void k_mark_excluded(const int32_t* __restrict__ raw_dst, const u8* __restrict__ raw_type, u32 begin, u32 end,
+                                const int32_t* __restrict__ new_of_old, int n, u32* __restrict__ excl) {
+    const u32 e = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < end && raw_type[e] == RWR_EDGE_LIKE) {
+        const int32_t d = raw_dst[e];
+        if (d >= 0 && d < n) {
+            const int j = new_of_old[d];
+            atomicOr(&excl[j >> 5], 1u << (j & 31));
+        }
+    }
+}
+
+// ---- full ranking helpers
+__global__ void k_item_flags(const u8* __restrict__ type_int, int n, u32* __restrict__ flags) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) flags[j] = type_int[j] == RWR_NODE_ITEM;
+}
+__global__ void k_item_keys(const u8* __restrict__ type_int, const int64_t* __restrict__ id_int, const u32* __restrict__ pos,
+                            int n, u64* __restrict__ keys, u32* __restrict__ vals) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && type_int[j] == RWR_NODE_ITEM) {
+        const u64 asc = (u64)id_int[j] ^ 0x8000000000000000ULL;   // signed order -> unsigned order
+        keys[pos[j]] = ~asc;                                      // ascending sort == id descending
+        vals[pos[j]] = (u32)j;
+    }
+}
+__global__ void k_cand_flags(const int32_t* __restrict__ items, int n_items, const u32* __restrict__ excl, u32* __restrict__ flags) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_items) {
+        const int j = items[p];
+        flags[p] = !((excl[j >> 5] >> (j & 31)) & 1u);
+    }
+}
+template <typename T>
+__global__ void k_cand_keys(const int32_t* __restrict__ items, int n_items, const u32* __restrict__ excl,
+                            const u32* __restrict__ pos, const T* __restrict__ y, u64* __restrict__ keys, u32* __restrict__ vals) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_items) {
+        const int j = items[p];
+        if (!((excl[j >> 5] >> (j & 31)) & 1u)) {
+            keys[pos[p]] = ~score_key((double)y[j]);              // ascending sort == score descending
+            vals[pos[p]] = (u32)j;
+        }
+    }
+}
+template <typename T>
+__global__ void k_emit_ranking(const u32* __restrict__ order, size_t count, const T* __restrict__ y,
+                               const int64_t* __restrict__ id_int, int64_t* __restrict__ ids, double* __restrict__ scores) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < count) {
+        const u32 j = order[p];
+        ids[p] = id_int[j];
+        scores[p] = (double)y[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static void seed_raw_range(rwr_graph* g, int seed, u32* begin, u32* end) {
+    u32 rp[2];
+    CUDA_CHECK(cudaMemcpyAsync(rp, g->raw_ptr.p + seed, 2 * sizeof(u32), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    *begin = rp[0];
+    *end = rp[1];
+}
+
+static void mark_excluded(rwr_graph* g, int seed, u32* excl, size_t words) {
+    if (seed < 0 || seed >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
+    u32 b, e;
+    seed_raw_range(g, seed, &b, &e);
+    if (b == e) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
+    CUDA_CHECK(cudaMemsetAsync(excl, 0, words * sizeof(u32), g->stream));
+    k_mark_excluded<<<div_up(e - b, 256), 256, 0, g->stream>>>(g->raw_dst.p, g->raw_type.p, b, e, g->new_of_old.p, g->n, excl);
+    KERNEL_CHECK();
+    g->pool.launches += 1;
+}
+
+template <typename T>
+static void topk_one(rwr_graph* g, const T* y, int seed, int k, u32* excl, size_t words, Cand* block_out, int grid,
+                     int64_t* d_ids, double* d_scores, int* d_count) {
+    mark_excluded(g, seed, excl, words);
+    k_topk_scan<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, g->node_type_int.p, g->node_id_int.p, excl, g->n, k, block_out);
+    k_topk_merge<T><<<1, TOPK_THREADS, 0, g->stream>>>(block_out, grid * k, k, y, d_ids, d_scores, d_count);
+    KERNEL_CHECK();
+    g->pool.launches += 2;
+}
+
+static void ensure_items_by_id(rwr_graph* g) {
+    if (g->items_by_id_desc.p) return;
+    cudaStream_t st = g->stream;
+    const int n = g->n;
+    DevBuf<u32> pos, total;
+    pos.alloc(n); total.alloc(1);
+    if (n) k_item_flags<<<div_up(n, 256), 256, 0, st>>>(g->node_type_int.p, n, pos.p);
+    KERNEL_CHECK();
+    prim::exclusive_scan<u32>(pos.p, pos.p, n, total.p, st, &g->pool);
+    u32 m = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&m, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    DevBuf<u64> k0, k1;
+    DevBuf<u32> v0, v1;
+    k0.alloc(m); k1.alloc(m); v0.alloc(m); v1.alloc(m);
+    if (n) k_item_keys<<<div_up(n, 256), 256, 0, st>>>(g->node_type_int.p, g->node_id_int.p, pos.p, n, k0.p, v0.p);
+    KERNEL_CHECK();
+    bool fl = prim::radix_sort<u64>(k0.p, k1.p, v0.p, v1.p, m, 64, st, &g->pool);
+    g->items_by_id_desc.alloc(m, &g->pool);
+    if (m) CUDA_CHECK(cudaMemcpyAsync(g->items_by_id_desc.p, fl ? v1.p : v0.p, (size_t)m * 4, cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    g->n_items = (int)m;
+}
+
+// Full ranking of one seed on the device; returns the candidate count, fills up to `cap` pairs on the host.
+template <typename T>
+static int64_t rank_all_one(rwr_graph* g, const T* y, int seed, int64_t* ids, double* scores, int64_t cap) {
+    cudaStream_t st = g->stream;
+    ensure_items_by_id(g);
+    const size_t words = ((size_t)g->n + 31) / 32 + 1;
+    DevBuf<u32> excl;
+    excl.alloc(words);
+    mark_excluded(g, seed, excl.p, words);
+    const int m = g->n_items;
+    DevBuf<u32> pos, total;
+    pos.alloc(m); total.alloc(1);
+    if (m) k_cand_flags<<<div_up(m, 256), 256, 0, st>>>(g->items_by_id_desc.p, m, excl.p, pos.p);
+    KERNEL_CHECK();
+    prim::exclusive_scan<u32>(pos.p, pos.p, m, total.p, st, &g->pool);
+    u32 cnt = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&cnt, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (cnt == 0) return 0;
+    DevBuf<u64> k0, k1;
+    DevBuf<u32> v0, v1;
+    k0.alloc(cnt); k1.alloc(cnt); v0.alloc(cnt); v1.alloc(cnt);
+    k_cand_keys<T><<<div_up(m, 256), 256, 0, st>>>(g->items_by_id_desc.p, m, excl.p, pos.p, y, k0.p, v0.p);
+    KERNEL_CHECK();
+    bool fl = prim::radix_sort<u64>(k0.p, k1.p, v0.p, v1.p, cnt, 64, st, &g->pool);
+    const size_t emit = (size_t)std::min<int64_t>(cap, (int64_t)cnt);
+    if (emit && ids && scores) {
+        DevBuf<int64_t> d_ids;
+        DevBuf<double> d_sc;
+        d_ids.alloc(emit); d_sc.alloc(emit);
+        k_emit_ranking<T><<<div_up(emit, 256), 256, 0, st>>>(fl ? v1.p : v0.p, emit, y, g->node_id_int.p, d_ids.p, d_sc.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(ids, d_ids.p, emit * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(scores, d_sc.p, emit * 8, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    g->pool.launches += 3;
+    return (int64_t)cnt;
+}
+
+extern "C" {
+
+int rwr_topk(rwr_result* r, int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts) {
+    RWR_API_BEGIN
+    if (!r || !out_ids || !out_scores || !out_counts) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    if (k <= 0) RWR_FAIL(RWR_E_INVALID, "k must be positive (Recommendation(.., topN <= 0) returns the full list: use rwr_rank_all)");
+    rwr_graph* g = r->g;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    const int S = r->n_seeds;
+    if (k > TOPK_MAX) {                                  // large k: truncate the full ranking
+        for (int s = 0; s < S; s++) {
+            int64_t cnt = (r->precision == RWR_FP64)
+                ? rank_all_one<double>(g, r->y64.p + (size_t)s * r->ld, r->seeds[s], out_ids + (size_t)s * k, out_scores + (size_t)s * k, k)
+                : rank_all_one<float>(g, r->y32.p + (size_t)s * r->ld, r->seeds[s], out_ids + (size_t)s * k, out_scores + (size_t)s * k, k);
+            out_counts[s] = (int32_t)std::min<int64_t>(cnt, k);
+        }
+        return RWR_OK;
+    }
+    const size_t words = ((size_t)g->n + 31) / 32 + 1;
+    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up((size_t)std::max(g->n, 1), TOPK_THREADS)));
+    DevBuf<u32> excl;
+    DevBuf<Cand> block_out;
+    DevBuf<int64_t> d_ids;
+    DevBuf<double> d_sc;
+    DevBuf<int> d_cnt;
+    excl.alloc(words); block_out.alloc((size_t)grid * k);
+    d_ids.alloc((size_t)S * k); d_sc.alloc((size_t)S * k); d_cnt.alloc(S);
+    CUDA_CHECK(cudaMemsetAsync(d_ids.p, 0, (size_t)S * k * 8, st));
+    CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)S * k * 8, st));
+    for (int s = 0; s < S; s++) {
+        if (r->precision == RWR_FP64)
+            topk_one<double>(g, r->y64.p + (size_t)s * r->ld, r->seeds[s], k, excl.p, words, block_out.p, grid,
+                             d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
+        else
+            topk_one<float>(g, r->y32.p + (size_t)s * r->ld, r->seeds[s], k, excl.p, words, block_out.p, grid,
+                            d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids.p, (size_t)S * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_scores, d_sc.p, (size_t)S * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_counts, d_cnt.p, (size_t)S * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_rank_all(rwr_result* r, int32_t seed_slot, int64_t* ids, double* scores, int64_t cap, int64_t* count) {
+    RWR_API_BEGIN
+    if (!r || !count) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    if (seed_slot < 0 || seed_slot >= r->n_seeds) RWR_FAIL(RWR_E_INVALID, "seed slot %d outside [0, %d)", seed_slot, r->n_seeds);
+    rwr_graph* g = r->g;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    if (cap < 0) cap = 0;
+    *count = (r->precision == RWR_FP64)
+        ? rank_all_one<double>(g, r->y64.p + (size_t)seed_slot * r->ld, r->seeds[seed_slot], ids, scores, cap)
+        : rank_all_one<float>(g, r->y32.p + (size_t)seed_slot * r->ld, r->seeds[seed_slot], ids, scores, cap);
+    return RWR_OK;
+    RWR_API_END
+}
+
+// n_seeds x Recommendation(seed, c, nIter, k).  Seeds are processed in tiles; ranks are not kept.
+int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int32_t n_iter, int32_t precision,
+                  int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts, rwr_run_info* info) {
+    RWR_API_BEGIN
+    if (!g || !out_ids || !out_scores || !out_counts || (n_seeds && !seeds)) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    if (k <= 0) RWR_FAIL(RWR_E_INVALID, "k must be positive");
+    if (info) memset(info, 0, sizeof(*info));
+    const int tile = std::max(1, g->opts.batch_width > 0 ? g->opts.batch_width : 8);
+    for (int s0 = 0; s0 < n_seeds; s0 += tile) {
+        const int cnt = std::min(tile, n_seeds - s0);
+        rwr_result* res = nullptr;
+        int rc = rwr_run_fixed(g, seeds + s0, cnt, c, n_iter, precision, &res);
+        if (rc != RWR_OK) return rc;
+        rc = rwr_topk(res, k, out_ids + (size_t)s0 * k, out_scores + (size_t)s0 * k, out_counts + s0);
+        if (info) {
+            info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = precision; info->iterations = n_iter;
+            info->residual = NAN; info->iterate_ms += res->iterate_ms; info->total_ms += res->total_ms;
+            info->kernel_launches += res->launches + 3 * cnt;
+        }
+        rwr_result_destroy(res);
+        if (rc != RWR_OK) return rc;
+    }
+    return RWR_OK;
+    RWR_API_END
+}
+
+// Experiment.cs:121-128 (+ :136): hits and average precision of a ranking against the held-out set
+int rwr_evaluate(const int64_t* ranked_ids, int64_t n, const int64_t* test_ids, int64_t n_test, int32_t* hits,
+                 double* avg_precision) {
+    RWR_API_BEGIN
+    if ((n && !ranked_ids) || (n_test && !test_ids) || !hits || !avg_precision || n < 0 || n_test < 0)
+        RWR_FAIL(RWR_E_INVALID, "bad argument");
+    std::unordered_set<int64_t> test(test_ids, test_ids + n_test);
+    int nHits = 0;
+    double sumPrecision = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (test.count(ranked_ids[i])) {
+            nHits += 1;
+            sumPrecision += (double)nHits / (double)(i + 1);
+        }
+    }
+    *hits = nHits;
+    *avg_precision = nHits == 0 ? 0.0 : sumPrecision / nHits;
+    return RWR_OK;
+    RWR_API_END
+}
+
+}  // extern "C"

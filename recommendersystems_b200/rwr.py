@@ -1,0 +1,355 @@
+"""Host-side mirror of `Recommenders.RWRBased` (reference: Recommenders/RWRBased/{Graph,Model,Recommender}.cs).
+
+Same names, argument meaning and error behaviour as the C# classes; every computation is forwarded through the
+C ABI of librwr_b200.so (include/rwr_b200.h) -- the same entry points the C# P/Invoke shim binds
+(recommendersystems_b200/csharp/RwrNative.cs).  Exceptions map the reference's:
+    KeyError    <- KeyNotFoundException   (seed without an `edges` entry, Recommender.cs:21; graph not built, Model.cs:79)
+    ValueError  <- ArgumentException      (buildGraph() twice, Graph.cs:86)
+    IndexError  <- IndexOutOfRangeException (link target outside the node range, Model.cs:87)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+
+FP64, FP32 = N.FP64, N.FP32
+
+
+class NodeType(enum.IntEnum):      # Recommender.cs:4
+    UNDEFINED = 0
+    USER = 1
+    ITEM = 2
+    ETC = 3
+
+
+class EdgeType(enum.IntEnum):      # Recommender.cs:5
+    UNDEFINED = 0
+    LIKE = 1
+    FRIENDSHIP = 2
+    FOLLOW = 3
+    MENTION = 4
+    AUTHORSHIP = 5
+    PURCHASE = 6
+    ETC = 7
+
+
+class RwrError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"librwr_b200 error {code}: {msg}")
+        self.code = code
+
+
+def _check(rc: int) -> None:
+    if rc == N.RWR_OK:
+        return
+    msg = N.last_error()
+    if rc in (N.RWR_E_BADSEED, N.RWR_E_NOT_BUILT):
+        raise KeyError(msg)
+    if rc == N.RWR_E_ALREADY_BUILT:
+        raise ValueError(msg)
+    if rc == N.RWR_E_BADINDEX:
+        raise IndexError(msg)
+    raise RwrError(rc, msg)
+
+
+def widen_float(x: float) -> float:
+    """`float dampingFactor` widened to double, as Recommender.cs:16 does implicitly (0.15f -> 0.15000000596046448)."""
+    return float(np.float32(x))
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Node:                         # Graph.cs:4-17
+    __slots__ = ("id", "type")
+
+    def __init__(self, id: int, type: int = NodeType.UNDEFINED):
+        self.id = int(id)
+        self.type = int(type)
+
+
+class ForwardLink:                  # Graph.cs:19-35
+    __slots__ = ("targetNode", "type", "weight")
+
+    def __init__(self, targetNode: int, type: int = EdgeType.UNDEFINED, weight: float = 1.0):
+        self.targetNode = int(targetNode)
+        self.type = int(type)
+        self.weight = float(weight)
+
+    def __repr__(self):
+        return f"ForwardLink({self.targetNode}, {self.type}, {self.weight!r})"
+
+
+class SynthSpec(dict):
+    """Keyword bag for rwr_synth_spec (include/rwr_b200.h)."""
+    FIELDS = ("seed", "n_users", "n_items", "n_third", "authorship_per_mille", "n_like", "n_friend", "n_follow",
+              "n_mention", "undefined_per_mille", "scramble", "p1_byte", "reserved")
+
+    def to_c(self) -> N.rwr_synth_spec:
+        d = dict(n_third=0, authorship_per_mille=1000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
+                 p1_byte=61, reserved=0)
+        d.update(self)
+        return N.rwr_synth_spec(**{k: int(d[k]) for k in self.FIELDS})
+
+
+def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_width=0, stream=0) -> N.rwr_opts:
+    return N.rwr_opts(device=int(device), layout=int(layout), relabel=0 if relabel else 1, hub_entries=int(hub_entries),
+                      batch_width=int(batch_width), reserved0=0, stream=int(stream))
+
+
+class Graph:
+    """Graph.cs:37-94.  `nodes`: Dictionary<int, Node>; `edges`: Dictionary<int, List<ForwardLink>>."""
+
+    def __init__(self, nodes: Optional[Dict[int, Node]] = None, edges: Optional[Dict[int, List[ForwardLink]]] = None,
+                 **opts):
+        self._h = C.c_void_p()
+        self._opts = opts
+        self.nodes = nodes
+        self.edges = edges
+        if nodes is not None:
+            n = len(nodes)
+            node_id = np.fromiter((nodes[i].id for i in range(n)), np.int64, n)
+            node_type = np.fromiter((nodes[i].type for i in range(n)), np.int32, n)
+            src, dst, et, w = [], [], [], []
+            for i in range(n):                          # `for i in 0..N-1: foreach l in edges[i]`
+                for l in (edges or {}).get(i, ()):
+                    src.append(i); dst.append(l.targetNode); et.append(l.type); w.append(l.weight)
+            self._create(node_id, node_type, np.asarray(src, np.int32), np.asarray(dst, np.int32),
+                         np.asarray(et, np.int32), np.asarray(w, np.float64))
+
+    # -- construction -------------------------------------------------------------------------------------------
+    def _create(self, node_id, node_type, src, dst, etype, w):
+        node_id = np.ascontiguousarray(node_id, np.int64)
+        node_type = np.ascontiguousarray(node_type, np.int32)
+        src = np.ascontiguousarray(src, np.int32)
+        dst = np.ascontiguousarray(dst, np.int32)
+        etype = np.ascontiguousarray(etype, np.int32)
+        w = np.ascontiguousarray(w, np.float64)
+        if not (len(src) == len(dst) == len(etype) == len(w)) or len(node_id) != len(node_type):
+            raise ValueError("array lengths differ")
+        o = _opts(**self._opts)
+        _check(N.lib().rwr_graph_create(len(node_id), _p(node_id), _p(node_type), len(src), _p(src), _p(dst), _p(etype),
+                                        _p(w), C.byref(o), C.byref(self._h)))
+
+    @classmethod
+    def from_arrays(cls, node_id, node_type, src, dst, etype, w, **opts) -> "Graph":
+        """Flattened SoA form of (nodes, edges): links grouped by source in insertion order."""
+        g = cls(None, None, **opts)
+        g._create(node_id, node_type, src, dst, etype, w)
+        return g
+
+    @classmethod
+    def synthetic(cls, spec: dict, **opts) -> "Graph":
+        """Deterministic synthetic graph generated on the device (replaces DataLoader + SQLite)."""
+        g = cls(None, None, **opts)
+        s = SynthSpec(spec).to_c()
+        o = _opts(**opts)
+        _check(N.lib().rwr_synth_create(C.byref(s), C.byref(o), C.byref(g._h)))
+        return g
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().rwr_graph_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- reference surface --------------------------------------------------------------------------------------
+    def buildGraph(self) -> None:
+        _check(N.lib().rwr_graph_build(self._h))
+
+    def size(self) -> int:
+        return self.info().n_nodes
+
+    # -- probes -------------------------------------------------------------------------------------------------
+    def info(self) -> N.rwr_graph_info:
+        i = N.rwr_graph_info()
+        _check(N.lib().rwr_graph_get_info(self._h, C.byref(i)))
+        return i
+
+    def csr(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """`Graph.graph` as (row_ptr[N+1], targetNode[nnz], weight[nnz]); null rows are empty."""
+        i = self.info()
+        if not i.built:
+            raise KeyError("buildGraph() has not run")
+        rp = np.empty(i.n_nodes + 1, np.int64)
+        col = np.empty(i.nnz, np.int32)
+        val = np.empty(i.nnz, np.float64)
+        _check(N.lib().rwr_graph_get_csr(self._h, _p(rp), _p(col), _p(val)))
+        return rp, col, val
+
+    def degrees(self, raw: bool = False) -> np.ndarray:
+        n = self.info().n_nodes
+        d = np.empty(n, np.int32)
+        if raw:
+            _check(N.lib().rwr_graph_get_degrees(self._h, None, _p(d)))
+        else:
+            _check(N.lib().rwr_graph_get_degrees(self._h, _p(d), None))
+        return d
+
+    def export_links(self) -> dict:
+        i = self.info()
+        out = dict(node_id=np.empty(i.n_nodes, np.int64), node_type=np.empty(i.n_nodes, np.int32),
+                   src=np.empty(i.n_links_raw, np.int32), dst=np.empty(i.n_links_raw, np.int32),
+                   etype=np.empty(i.n_links_raw, np.int32), w=np.empty(i.n_links_raw, np.float64))
+        _check(N.lib().rwr_graph_export_links(self._h, _p(out["node_id"]), _p(out["node_type"]), _p(out["src"]),
+                                              _p(out["dst"]), _p(out["etype"]), _p(out["w"])))
+        return out
+
+
+class _Result:
+    def __init__(self, h: C.c_void_p, n_seeds: int, n_nodes: int, graph: "Graph"):
+        self._h, self.n_seeds, self.n_nodes = h, n_seeds, n_nodes
+        self._graph = graph               # keeps the native graph alive for as long as its results exist
+
+    def close(self):
+        if self._h is not None and self._h.value:
+            N.lib().rwr_result_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def info(self) -> N.rwr_run_info:
+        i = N.rwr_run_info()
+        _check(N.lib().rwr_result_get_info(self._h, C.byref(i)))
+        return i
+
+    def scores(self, slot: int = 0) -> np.ndarray:
+        out = np.empty(self.n_nodes, np.float64)
+        _check(N.lib().rwr_scores(self._h, slot, _p(out)))
+        return out
+
+    def topk(self, k: int):
+        ids = np.zeros((self.n_seeds, k), np.int64)
+        sc = np.zeros((self.n_seeds, k), np.float64)
+        cnt = np.zeros(self.n_seeds, np.int32)
+        _check(N.lib().rwr_topk(self._h, k, _p(ids), _p(sc), _p(cnt)))
+        return ids, sc, cnt
+
+    def rank_all(self, slot: int = 0, cap: Optional[int] = None):
+        cap = self.n_nodes if cap is None else cap
+        ids = np.empty(cap, np.int64)
+        sc = np.empty(cap, np.float64)
+        cnt = C.c_int64()
+        _check(N.lib().rwr_rank_all(self._h, slot, _p(ids), _p(sc), cap, C.byref(cnt)))
+        m = min(cnt.value, cap)
+        return ids[:m], sc[:m], cnt.value
+
+
+def run_fixed(graph: Graph, seeds: Sequence[int], c: float, n_iter: int, precision: int = FP64) -> _Result:
+    s = np.ascontiguousarray(seeds, np.int32)
+    h = C.c_void_p()
+    _check(N.lib().rwr_run_fixed(graph._h, _p(s), len(s), float(c), int(n_iter), precision, C.byref(h)))
+    return _Result(h, len(s), graph.size(), graph)
+
+
+def run_threshold(graph: Graph, seeds: Sequence[int], c: float, thr: float, max_iter: int = 0, precision: int = FP64):
+    s = np.ascontiguousarray(seeds, np.int32)
+    it = np.zeros(len(s), np.int32)
+    h = C.c_void_p()
+    _check(N.lib().rwr_run_threshold(graph._h, _p(s), len(s), float(c), float(thr), int(max_iter), precision, _p(it),
+                                     C.byref(h)))
+    return _Result(h, len(s), graph.size(), graph), it
+
+
+class Model:
+    """Model.cs:5-116.  `Model(graph, d)` = uniform restart, `Model(graph, d, targetNode)` = seeded."""
+
+    def __init__(self, graph: Graph, dampingFactor: float, targetNode: Optional[int] = None, precision: int = FP64):
+        self.graph = graph
+        self.nNodes = graph.size()
+        self.dampingFactor = float(dampingFactor)
+        self.targetNode = targetNode
+        self.precision = precision
+        self.nIterations = 0              # deliverRanks() calls so far
+        self._fixed_total = 0
+        self._res: Optional[_Result] = None
+        self.residual = float("nan")
+
+    def _seed(self) -> int:
+        return -1 if self.targetNode is None else int(self.targetNode)
+
+    def run(self, arg=None, max_iter: int = 0) -> None:
+        """run(int nIterations) / run(double threshold) / run() -- Model.cs:68-73, :57-66, :52-55."""
+        if isinstance(arg, (int, np.integer)) and not isinstance(arg, bool):
+            # successive run(int) calls accumulate in the reference; re-run from the constructor state
+            self._fixed_total += max(int(arg), 0)
+            self._res = run_fixed(self.graph, [self._seed()], self.dampingFactor, self._fixed_total, self.precision)
+            self.nIterations = self._fixed_total
+            return
+        if self._fixed_total:
+            raise NotImplementedError("threshold run after run(int) on the same Model is not supported")
+        thr = 0.0 if arg is None else float(arg)      # thr <= 0 selects Model.run(): (1/double.MaxValue) * N
+        self._res, it = run_threshold(self.graph, [self._seed()], self.dampingFactor, thr, max_iter, self.precision)
+        self.nIterations = int(it[0])
+        self.residual = self._res.info().residual
+
+    @property
+    def rank(self) -> np.ndarray:
+        if self._res is None:             # constructor state, Model.cs:24 / :44
+            r = np.ones(self.nNodes) if self.targetNode is None else np.zeros(self.nNodes)
+            if self.targetNode is not None and 0 <= self.targetNode < self.nNodes:
+                r[self.targetNode] = self.nNodes
+            return r
+        return self._res.scores(0)
+
+
+class Recommender:
+    """Recommender.cs:7-52."""
+
+    def __init__(self, graph: Graph, precision: int = FP64):
+        self.graph = graph
+        self.precision = precision
+        self.last_info = None
+
+    def Recommendation(self, idxTargetUser: int, dampingFactor: float, nIteration: int,
+                       topN: Optional[int] = None) -> List[Tuple[int, float]]:
+        """`dampingFactor` is the reference's C# float: it is widened to double here, as at Recommender.cs:16."""
+        c = widen_float(dampingFactor)
+        res = run_fixed(self.graph, [int(idxTargetUser)], c, int(nIteration), self.precision)
+        try:
+            self.last_info = res.info()
+            if topN is not None and topN > 0:
+                ids, sc, cnt = res.topk(int(topN))
+                m = int(cnt[0])
+                return list(zip(ids[0, :m].tolist(), sc[0, :m].tolist()))
+            # 3-argument overload; the 4-argument one returns the whole list too when topN <= 0 (Recommender.cs:47)
+            ids, sc, _ = res.rank_all(0)
+            return list(zip(ids.tolist(), sc.tolist()))
+        finally:
+            res.close()
+
+    def RecommendationBatch(self, seeds: Iterable[int], dampingFactor: float, nIteration: int, topN: int):
+        """n x Recommendation(seed, c, nIter, topN) through the fused tiled path -> (ids[n,k], scores[n,k], counts[n])."""
+        s = np.ascontiguousarray(list(seeds), np.int32)
+        ids = np.zeros((len(s), topN), np.int64)
+        sc = np.zeros((len(s), topN), np.float64)
+        cnt = np.zeros(len(s), np.int32)
+        info = N.rwr_run_info()
+        _check(N.lib().rwr_recommend(self.graph._h, _p(s), len(s), widen_float(dampingFactor), int(nIteration),
+                                     self.precision, int(topN), _p(ids), _p(sc), _p(cnt), C.byref(info)))
+        self.last_info = info
+        return ids, sc, cnt
+
+
+def evaluate(recommendation: Sequence[Tuple[int, float]], testSet: Iterable[int]) -> Tuple[int, float]:
+    """Experiment.cs:121-128, :136 -> (nHits, averagePrecision)."""
+    ids = np.ascontiguousarray([p[0] for p in recommendation], np.int64)
+    t = np.ascontiguousarray(list(testSet), np.int64)
+    hits, ap = C.c_int32(), C.c_double()
+    _check(N.lib().rwr_evaluate(_p(ids), len(ids), _p(t), len(t), C.byref(hits), C.byref(ap)))
+    return hits.value, ap.value

@@ -1,0 +1,405 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI via the host mirror of
+the reference API, against the golden fixtures and the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star):
+  CSR structure, degrees and normalised weights ........ bit-exact
+  iteration count under the same threshold ............. identical
+  FP64 per-node scores ................................. <= 1e-12 relative (zeros exactly zero)
+  FP32 scores .......................................... <= 1e-6 L1 on sum=1-normalised scores
+  top-k / full ranking ................................. identical id lists (ties inside the tolerance excepted)
+"""
+import numpy as np
+import pytest
+
+from conftest import C1_SPEC, bits, load_golden, unhex
+
+pytestmark = pytest.mark.gpu
+
+import oracle as O
+import recommendersystems_b200 as rs
+from recommendersystems_b200 import _native as N
+from recommendersystems_b200.rwr import run_fixed, run_threshold
+
+REL = 1e-12            # FP64 tolerance stated by north_star
+L1_FP32 = 1e-6         # FP32 tolerance stated by north_star
+C015 = rs.widen_float(0.15)
+
+CASES = ["kat_8c", "small_a", "small_b"]
+OPTS = [dict(), dict(relabel=False), dict(hub_entries=0), dict(relabel=False, hub_entries=0, layout=N.LAYOUT_VALUED)]
+
+
+def assert_close_fp64(got, want, what=""):
+    got, want = np.asarray(got), np.asarray(want)
+    zero = want == 0.0
+    assert np.all(got[zero] == 0.0), f"{what}: nodes the reference leaves at exactly 0 must stay 0"
+    rel = np.abs(got[~zero] - want[~zero]) / np.abs(want[~zero])
+    assert rel.size == 0 or rel.max() <= REL, f"{what}: max rel err {rel.max():.3e}"
+
+
+def assert_close_fp32(got, want, what=""):
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    l1 = np.abs(got / got.sum() - want / want.sum()).sum()
+    assert l1 <= L1_FP32, f"{what}: normalised L1 {l1:.3e}"
+
+
+def same_ranking(ids, scores, want_ids, want_scores):
+    """Identical lists, except that positions whose reference scores agree within REL may be permuted."""
+    ids, want_ids = list(ids), list(want_ids)
+    assert len(ids) == len(want_ids)
+    if ids == want_ids:
+        return
+    want_scores = np.asarray(want_scores)
+    i = 0
+    while i < len(ids):
+        j = i + 1
+        while j < len(ids) and abs(want_scores[j] - want_scores[i]) <= REL * max(abs(want_scores[i]), 1e-300):
+            j += 1
+        assert sorted(ids[i:j]) == sorted(want_ids[i:j]), f"ranking differs outside a tie group at {i}"
+        i = j
+
+
+def gpu_graph(inp, **opts):
+    g = rs.Graph.from_arrays(inp["node_id"], inp["node_type"], inp["src"], inp["dst"], inp["etype"], inp["w"], **opts)
+    g.buildGraph()
+    return g
+
+
+def oracle_graph(inp):
+    og = O.OracleGraph(inp["node_id"], inp["node_type"], inp["src"], inp["dst"], inp["etype"], inp["w"])
+    assert og.build() == 0
+    return og
+
+
+# ------------------------------------------------------------------------------------------ golden fixtures
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("opts", OPTS)
+def test_golden_csr_bit_exact(name, opts):
+    g = load_golden(name)
+    gg = gpu_graph(g["input"], **opts)
+    rp, col, val = gg.csr()
+    assert rp.tolist() == g["csr"]["row_ptr"]
+    assert col.tolist() == g["csr"]["col"]
+    assert np.array_equal(bits(val), bits(unhex(g["csr"]["val"])))
+    assert gg.degrees().tolist() == g["outdeg"]
+    with pytest.raises(ValueError):                      # ArgumentException, Graph.cs:86
+        gg.buildGraph()
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("opts", OPTS)
+def test_golden_ranks_fp64(name, opts):
+    g = load_golden(name)
+    gg = gpu_graph(g["input"], **opts)
+    for e in g["seeds"]:
+        for n, want in e["ranks"].items():
+            m = rs.Model(gg, C015, e["seed"])
+            m.run(int(n))
+            assert_close_fp64(m.rank, unhex(want), f"{name} seed {e['seed']} iter {n}")
+            assert abs(m.rank.sum() - gg.size()) <= 1e-12 * gg.size()      # mass conservation
+    # zero iterations == constructor state
+    m = rs.Model(gg, C015, g["seeds"][0]["seed"])
+    m.run(0)
+    want = np.zeros(gg.size()); want[g["seeds"][0]["seed"]] = gg.size()
+    assert np.array_equal(m.rank, want)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_threshold_iteration_counts(name):
+    g = load_golden(name)
+    gg = gpu_graph(g["input"])
+    for e in g["seeds"]:
+        for thr, want in e["thresholds"].items():
+            if thr == "default":
+                continue          # subnormal threshold: stops only at a bitwise fixed point, order dependent
+            m = rs.Model(gg, C015, e["seed"])
+            m.run(float(thr))
+            assert m.nIterations == want["iters"], (name, e["seed"], thr)
+            assert_close_fp64(m.rank, unhex(want["rank"]), f"{name} seed {e['seed']} thr {thr}")
+
+
+def test_default_threshold_terminates_on_fixed_point():
+    g = load_golden("kat_8c")
+    gg = gpu_graph(g["input"])
+    m = rs.Model(gg, C015, 5)          # dangling seed: rank never moves, residual is exactly 0 < subnormal threshold
+    m.run()
+    assert m.nIterations == 1
+    m = rs.Model(gg, C015, 0)
+    m.run(None, max_iter=500)
+    assert 40 <= m.nIterations <= 500
+
+
+@pytest.mark.parametrize("name", CASES)
+@pytest.mark.parametrize("opts", OPTS[:2])
+def test_golden_recommendation(name, opts):
+    g = load_golden(name)
+    gg = gpu_graph(g["input"], **opts)
+    rec = rs.Recommender(gg)
+    for e in g["seeds"]:
+        if e["recommendation"] == "KeyNotFoundException":
+            with pytest.raises(KeyError):
+                rec.Recommendation(e["seed"], 0.15, 10)
+            with pytest.raises(KeyError):
+                rec.Recommendation(e["seed"], 0.15, 10, 3)
+            continue
+        want = e["recommendation"]
+        full = rec.Recommendation(e["seed"], 0.15, want["n_iter"])
+        same_ranking([p[0] for p in full], [p[1] for p in full], want["ids"], unhex(want["scores"]))
+        assert_close_fp64([p[1] for p in full], unhex(want["scores"]))
+        for k, w in e["top"].items():
+            top = rec.Recommendation(e["seed"], 0.15, want["n_iter"], int(k))
+            same_ranking([p[0] for p in top], [p[1] for p in top], w["ids"], unhex(w["scores"]))
+        whole = rec.Recommendation(e["seed"], 0.15, want["n_iter"], 0)      # Recommender.cs:47 quirk
+        assert len(whole) == len(want["ids"])
+        big = rec.Recommendation(e["seed"], 0.15, want["n_iter"], 10 ** 6)
+        assert [p[0] for p in big] == [p[0] for p in full]
+        k20 = rec.Recommendation(e["seed"], 0.15, want["n_iter"], 20)        # k > 16: truncated full ranking
+        assert [p[0] for p in k20] == [p[0] for p in full][:20]
+
+
+def test_kat_8c_spelled_out():
+    g = load_golden("kat_8c")
+    gg = gpu_graph(g["input"])
+    rec = rs.Recommender(gg).Recommendation(0, 0.15, 10)
+    assert [p[0] for p in rec] == [5004, 5003, 5006, 5005]
+    assert rec[2][1] == 0.0 and rec[3][1] == 0.0
+    assert abs(rec[0][1] - 0.39846507114785384) <= REL and rec[0][1] == rec[1][1]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_uniform_ctor(name):
+    g = load_golden(name)
+    gg = gpu_graph(g["input"])
+    for n, want in g["uniform"].items():
+        m = rs.Model(gg, C015)
+        m.run(int(n))
+        want = unhex(want)
+        assert np.abs(m.rank - want).max() <= 1e-12 * np.abs(want).max()
+
+
+def test_golden_fp32():
+    for name in CASES:
+        g = load_golden(name)
+        gg = gpu_graph(g["input"])
+        for e in g["seeds"]:
+            n = max(int(k) for k in e["ranks"])
+            m = rs.Model(gg, C015, e["seed"], precision=rs.FP32)
+            m.run(n)
+            assert_close_fp32(m.rank, unhex(e["ranks"][str(n)]), f"{name} seed {e['seed']}")
+
+
+def test_error_codes():
+    g = load_golden("kat_8c")
+    inp = dict(g["input"])
+    gg = rs.Graph.from_arrays(inp["node_id"], inp["node_type"], inp["src"], inp["dst"], inp["etype"], inp["w"])
+    with pytest.raises(KeyError):                      # Model before buildGraph: KeyNotFound at Model.cs:79
+        run_fixed(gg, [0], C015, 1)
+    et = list(inp["etype"])
+    i_exp, i_und = et.index(1), et.index(0)
+    bad = dict(inp); bad["dst"] = list(inp["dst"]); bad["dst"][i_exp] = 99
+    g2 = rs.Graph.from_arrays(bad["node_id"], bad["node_type"], bad["src"], bad["dst"], bad["etype"], bad["w"])
+    with pytest.raises(IndexError):                    # IndexOutOfRange at Model.cs:87
+        g2.buildGraph()
+    bad["dst"][i_exp] = inp["dst"][i_exp]; bad["dst"][i_und] = 99   # the UNDEFINED link: never dereferenced by the reference
+    g3 = rs.Graph.from_arrays(bad["node_id"], bad["node_type"], bad["src"], bad["dst"], bad["etype"], bad["w"])
+    g3.buildGraph()
+    gg.buildGraph()
+    with pytest.raises(KeyError):
+        run_fixed(gg, [8], C015, 1)
+    with pytest.raises(rs.RwrError):
+        run_fixed(gg, [0], C015, 1, precision=7)
+
+
+def test_empty_and_degenerate_graphs():
+    g0 = rs.Graph.from_arrays([], [], [], [], [], [])
+    g0.buildGraph()
+    assert g0.size() == 0 and g0.csr()[0].tolist() == [0]
+    # nodes without any link: every row dangling, rank stays put
+    g1 = rs.Graph.from_arrays([10, 20, 30], [1, 2, 2], [], [], [], [])
+    g1.buildGraph()
+    m = rs.Model(g1, C015, 1); m.run(5)
+    assert m.rank.tolist() == [0.0, 3.0, 0.0]
+    # a row whose weights sum to 0 silently yields NaN (Graph.cs:81) -- no error
+    g2 = rs.Graph.from_arrays([10, 20], [1, 2], [0, 0], [1, 1], [1, 5], [1.0, -1.0])
+    g2.buildGraph()
+    assert np.isinf(g2.csr()[2]).all()
+    g3 = rs.Graph.from_arrays([10, 20], [1, 2], [0], [1], [1], [0.0])
+    g3.buildGraph()
+    assert np.isnan(g3.csr()[2]).all()
+
+
+def test_unsorted_input_is_grouped_stably():
+    g = load_golden("small_b")
+    inp = g["input"]
+    rng = np.random.default_rng(3)
+    src = np.asarray(inp["src"])
+    # interleave links of different sources but keep every source's own order
+    perm = rng.permutation(len(src))
+    slots = np.argsort(src[perm], kind="stable")            # output slots grouped by source, ascending
+    order = np.empty(len(src), np.int64)
+    order[slots] = np.argsort(src, kind="stable")           # ... receive that source's links in their own order
+    sh = {k: np.asarray(inp[k])[order] for k in ("src", "dst", "etype", "w")}
+    gg = rs.Graph.from_arrays(inp["node_id"], inp["node_type"], sh["src"], sh["dst"], sh["etype"], sh["w"])
+    gg.buildGraph()
+    rp, col, val = gg.csr()
+    assert rp.tolist() == g["csr"]["row_ptr"] and col.tolist() == g["csr"]["col"]
+    assert np.array_equal(bits(val), bits(unhex(g["csr"]["val"])))
+
+
+# ------------------------------------------------------------------------------------------ synthetic generator
+def test_synth_generator_bit_exact_tiny():
+    g = load_golden("synth_tiny")
+    gg = rs.Graph.synthetic(g["spec"])
+    out = gg.export_links()
+    w = g["graph"]
+    for k in ("node_id", "node_type", "src", "dst", "etype"):
+        assert out[k].tolist() == w[k], k
+    assert np.array_equal(bits(out["w"]), bits(w["w"]))
+
+
+@pytest.fixture(scope="module")
+def c1():
+    cpu = O.synth_generate(C1_SPEC)
+    og = oracle_graph(cpu)
+    gg = rs.Graph.synthetic(C1_SPEC)
+    return cpu, og, gg
+
+
+def test_c1_generator_matches_oracle(c1):
+    cpu, og, gg = c1
+    out = gg.export_links()
+    for k in ("node_id", "node_type", "src", "dst", "etype"):
+        assert np.array_equal(out[k], cpu[k]), k
+    assert np.array_equal(bits(out["w"]), bits(cpu["w"]))
+    assert 80_000 <= len(cpu["src"]) <= 120_000 and og.n == 10_200
+
+
+def test_c1_csr_and_scores(c1):
+    cpu, og, gg = c1
+    if not gg.info().built:
+        gg.buildGraph()
+    rp, col, val = gg.csr()
+    orp, ocol, oval = og.csr()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(bits(val), bits(oval))
+    info = gg.info()
+    assert info.layout == N.LAYOUT_VALUED and info.n_dangling == int((np.diff(orp) == 0).sum())
+    raw_deg = np.bincount(cpu["src"], minlength=og.n)
+    seeds = [int(s) for s in np.flatnonzero((raw_deg > 0) & (np.arange(og.n) < C1_SPEC["n_users"]))[:3]]
+    seeds.append(int(np.argmax(raw_deg)))                         # the biggest hub
+    for seed in seeds:
+        for it in (1, 2, 5, 10, 20):
+            want, _ = og.run(seed, C015, n_iter=it)
+            m = rs.Model(gg, C015, seed); m.run(it)
+            assert_close_fp64(m.rank, want, f"C1 seed {seed} iter {it}")
+        want, _ = og.run(seed, C015, n_iter=20)
+        m32 = rs.Model(gg, C015, seed, precision=rs.FP32); m32.run(20)
+        assert_close_fp32(m32.rank, want, f"C1 fp32 seed {seed}")
+        ids, sc = og.recommend(seed, 0.15, 20, top_n=10)
+        top = rs.Recommender(gg).Recommendation(seed, 0.15, 20, 10)
+        same_ranking([p[0] for p in top], [p[1] for p in top], ids, sc)
+        fids, fsc = og.recommend(seed, 0.15, 20)
+        full = rs.Recommender(gg).Recommendation(seed, 0.15, 20)
+        same_ranking([p[0] for p in full], [p[1] for p in full], fids, fsc)
+        for thr in (1e-3 * og.n, 1e-6 * og.n, 1e-9 * og.n):
+            _, want_it = og.run(seed, C015, threshold=thr)
+            m = rs.Model(gg, C015, seed); m.run(thr)
+            assert m.nIterations == want_it, (seed, thr)
+    # batched request path
+    bids, bsc, bcnt = rs.Recommender(gg).RecommendationBatch(seeds, 0.15, 20, 10)
+    for i, seed in enumerate(seeds):
+        ids, sc = og.recommend(seed, 0.15, 20, top_n=10)
+        same_ranking(bids[i, :bcnt[i]], bsc[i, :bcnt[i]], ids, sc)
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(relabel=False), dict(hub_entries=0), dict(hub_entries=64), dict(layout=N.LAYOUT_VALUED)])
+def test_unit_weight_graph_uses_index_layout(opts):
+    """All raw weights 1.0 (the C2 shape): the row's weight folds into x, products stay bit-equal to the reference's."""
+    spec = dict(C1_SPEC, n_mention=0, seed=77)
+    cpu = O.synth_generate(spec)
+    og = oracle_graph(cpu)
+    gg = rs.Graph.synthetic(spec, **opts)
+    gg.buildGraph()
+    assert gg.info().layout == (N.LAYOUT_VALUED if opts.get("layout") == N.LAYOUT_VALUED else N.LAYOUT_INDEX)
+    rp, col, val = gg.csr()
+    orp, ocol, oval = og.csr()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(bits(val), bits(oval))
+    seed = int(np.argmax(np.bincount(cpu["src"], minlength=og.n)[:spec["n_users"]]))
+    for it in (1, 3, 20):
+        want, _ = og.run(seed, C015, n_iter=it)
+        m = rs.Model(gg, C015, seed); m.run(it)
+        assert_close_fp64(m.rank, want, f"unit seed {seed} iter {it} {opts}")
+    m32 = rs.Model(gg, C015, seed, precision=rs.FP32); m32.run(20)
+    assert_close_fp32(m32.rank, want)
+
+
+def test_index_layout_refused_for_fractional_rows():
+    gg = rs.Graph.synthetic(C1_SPEC, layout=N.LAYOUT_INDEX)
+    with pytest.raises(rs.RwrError) as ei:
+        gg.buildGraph()
+    assert ei.value.code == N.RWR_E_UNSUPPORTED
+
+
+# ------------------------------------------------------------------------------------------ hubs / chunk boundaries
+def test_medium_graph_hubs_cross_chunks():
+    """~1.2 M links, strong skew: hub rows span many merge-path chunks, lots of empty rows."""
+    spec = dict(seed=5, n_users=20_000, n_items=150_000, n_third=5_000, authorship_per_mille=500, n_like=450_000,
+                n_friend=120_000, n_follow=20_000, n_mention=3_000, undefined_per_mille=50, scramble=1, p1_byte=40)
+    cpu = O.synth_generate(spec)
+    og = oracle_graph(cpu)
+    for opts in (dict(), dict(relabel=False, hub_entries=0)):
+        gg = rs.Graph.synthetic(spec, **opts)
+        gg.buildGraph()
+        info = gg.info()
+        assert info.max_in_degree > 3 * 2044 and info.n_chunks > 300
+        rp, col, val = gg.csr()
+        orp, ocol, oval = og.csr()
+        assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(bits(val), bits(oval))
+        raw_deg = np.bincount(cpu["src"], minlength=og.n)
+        for seed in (int(np.argmax(raw_deg)), int(np.flatnonzero(raw_deg[:spec["n_users"]] == 1)[0])):
+            want, _ = og.run(seed, C015, n_iter=12)
+            m = rs.Model(gg, C015, seed); m.run(12)
+            assert_close_fp64(m.rank, want, f"medium seed {seed}")
+            ids, sc = og.recommend(seed, 0.15, 12, top_n=10)
+            top = rs.Recommender(gg).Recommendation(seed, 0.15, 12, 10)
+            same_ranking([p[0] for p in top], [p[1] for p in top], ids, sc)
+            thr = 1e-7 * og.n
+            _, want_it = og.run(seed, C015, threshold=thr)
+            m = rs.Model(gg, C015, seed); m.run(thr)
+            assert m.nIterations == want_it
+
+
+def test_determinism_and_full_size_properties():
+    """Size-independent properties on a 22 M-link graph (a 1/9 scale C2): mass conservation, bit-identical reruns,
+    FP32 vs FP64, ranking sortedness, index-only vs valued layouts bit-equal."""
+    spec = dict(seed=11, n_users=120_000, n_items=1_100_000, n_third=0, authorship_per_mille=1000, n_like=7_800_000,
+                n_friend=2_200_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1, p1_byte=61)
+    gg = rs.Graph.synthetic(spec)
+    gg.buildGraph()
+    info = gg.info()
+    n = info.n_nodes
+    assert info.layout == N.LAYOUT_INDEX and info.nnz > 19_000_000
+    deg = gg.degrees(raw=True)
+    seed = int(np.flatnonzero(deg[:spec["n_users"]] > 50)[0])
+    a = run_fixed(gg, [seed], C015, 20).scores(0)
+    b = run_fixed(gg, [seed], C015, 20).scores(0)
+    assert np.array_equal(bits(a), bits(b))
+    assert abs(a.sum() - n) <= 1e-11 * n and a.min() >= 0.0
+    f = run_fixed(gg, [seed], C015, 20, precision=rs.FP32).scores(0)
+    assert_close_fp32(f, a)
+    gv = rs.Graph.synthetic(spec, layout=N.LAYOUT_VALUED)
+    gv.buildGraph()
+    v = run_fixed(gv, [seed], C015, 20).scores(0)
+    assert np.array_equal(bits(a), bits(v))            # folding the row weight into x keeps every product bit-equal
+    res = run_fixed(gg, [seed], C015, 20)
+    ids, sc, cnt = res.rank_all(0)
+    assert cnt == len(ids) and np.all(np.diff(sc) <= 0)
+    ties = np.diff(sc) == 0
+    assert np.all(np.diff(ids)[ties] < 0)               # equal scores: id descending
+    tid, tsc, tcnt = res.topk(10)
+    assert tid[0, :tcnt[0]].tolist() == ids[:10].tolist()
+    # spot parity against the oracle on this size (collapsed form, a few seconds of CPU)
+    links = gg.export_links()
+    og = oracle_graph(links)
+    want, _ = og.run(seed, C015, n_iter=20)
+    assert_close_fp64(a, want, "22M-link graph")
+    oids, osc = og.recommend(seed, 0.15, 20, top_n=10)
+    same_ranking(tid[0, :tcnt[0]], tsc[0, :tcnt[0]], oids, osc)
