@@ -63,8 +63,10 @@ typedef struct rwr_opts {
     int32_t relabel;       /* 0 = auto (on): internal relabel by descending out-degree; 1 = off                 */
     int32_t hub_entries;   /* x entries staged in shared memory per CTA; -1 = auto, 0 = none                    */
     int32_t batch_width;   /* seed columns per SpMM tile; 0 = auto                                              */
-    int32_t reserved0;
+    int32_t kernel;        /* 0 = phased SpMV, 8 groups x 128 threads (default); 1 = pipelined producer/consumer variant */
     uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
+    int32_t hot_min_degree;/* nodes with fewer explicit links are clustered by first neighbour; 0 = auto (2), 1 = off */
+    int32_t reserved1;
 } rwr_opts;
 
 /* Deterministic synthetic generator (this repository's spec; replaces TweetRecommender/DataLoader.cs:256-436
@@ -88,6 +90,7 @@ typedef struct rwr_graph_info {
     int32_t n_dangling;      /* rows of W without explicit links (Graph.cs:53, :86 `null`)                      */
     int32_t layout;          /* RWR_LAYOUT_VALUED or RWR_LAYOUT_INDEX actually used                             */
     int32_t relabelled;
+    int32_t n_hot;           /* internal labels [0, n_hot) are the degree-sorted hot nodes                      */
     int32_t hub_entries_fp64, hub_entries_fp32;
     int32_t n_chunks;        /* merge-path work items of the SpMV                                               */
     int32_t max_in_degree, max_out_degree;

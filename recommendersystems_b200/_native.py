@@ -19,7 +19,8 @@ LAYOUT_AUTO, LAYOUT_VALUED, LAYOUT_INDEX = 0, 1, 2
 
 class rwr_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("relabel", C.c_int32), ("hub_entries", C.c_int32),
-                ("batch_width", C.c_int32), ("reserved0", C.c_int32), ("stream", C.c_uint64)]
+                ("batch_width", C.c_int32), ("kernel", C.c_int32), ("stream", C.c_uint64),
+                ("hot_min_degree", C.c_int32), ("reserved1", C.c_int32)]
 
 
 class rwr_synth_spec(C.Structure):
@@ -31,7 +32,7 @@ class rwr_synth_spec(C.Structure):
 
 class rwr_graph_info(C.Structure):
     _fields_ = [("n_nodes", C.c_int32), ("built", C.c_int32), ("n_links_raw", C.c_int64), ("nnz", C.c_int64),
-                ("n_dangling", C.c_int32), ("layout", C.c_int32), ("relabelled", C.c_int32),
+                ("n_dangling", C.c_int32), ("layout", C.c_int32), ("relabelled", C.c_int32), ("n_hot", C.c_int32),
                 ("hub_entries_fp64", C.c_int32), ("hub_entries_fp32", C.c_int32), ("n_chunks", C.c_int32),
                 ("max_in_degree", C.c_int32), ("max_out_degree", C.c_int32), ("build_ms", C.c_float),
                 ("synth_ms", C.c_float), ("device_bytes", C.c_int64)]

@@ -182,6 +182,42 @@ __global__ void k_invert_perm(const u32* __restrict__ old_of_new_u, int32_t n, i
     }
 }
 
+// cold == 1 <= out-degree < hot_min.  counts[0] = hot nodes, counts[1] = cold nodes
+__global__ void k_cold_flags(const u32* __restrict__ row_ptr, int32_t n, u32 hot_min, u32* __restrict__ flags, u32* counts) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 deg = row_ptr[i + 1] - row_ptr[i];
+    const u32 cold = deg >= 1 && deg < hot_min;
+    flags[i] = cold;
+    if (deg >= hot_min) atomicAdd(&counts[0], 1u);
+    else if (cold) atomicAdd(&counts[1], 1u);
+}
+
+// key of a cold node = label of its first out-neighbour when that one is hot, else n_hot + its original index
+__global__ void k_cold_keys(const u32* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                            const int32_t* __restrict__ new_of_old, int32_t n, u32 hot_min, u32 n_hot,
+                            const u32* __restrict__ pos, u32* __restrict__ keys, u32* __restrict__ vals) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 b = row_ptr[i], deg = row_ptr[i + 1] - b;
+    if (deg >= 1 && deg < hot_min) {
+        const int32_t nb = col[b];
+        const u32 lab = (u32)new_of_old[nb];
+        keys[pos[i]] = lab < n_hot ? lab : n_hot + (u32)nb;
+        vals[pos[i]] = (u32)i;
+    }
+}
+
+__global__ void k_assign_cold(const u32* __restrict__ sorted_ids, u32 n_cold, u32 n_hot, int32_t* __restrict__ new_of_old,
+                              int32_t* __restrict__ old_of_new) {
+    u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n_cold) {
+        const int32_t o = (int32_t)sorted_ids[p];
+        new_of_old[o] = (int32_t)(n_hot + p);
+        old_of_new[n_hot + p] = o;
+    }
+}
+
 __global__ void k_identity_perm(int32_t n, int32_t* a, int32_t* b) {
     int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < n) { a[j] = j; b[j] = j; }
@@ -391,10 +427,14 @@ static void graph_build_impl(rwr_graph* g) {
     if (layout != RWR_LAYOUT_INDEX && layout != RWR_LAYOUT_VALUED) RWR_FAIL(RWR_E_INVALID, "unknown layout %d", layout);
     g->layout = layout;
 
-    // ---- internal relabel by descending out-degree (== how often x_i is gathered)
+    // ---- internal relabel (locality): [hot nodes by descending out-degree == how often x_i is gathered]
+    //      ++ [cold nodes (out-degree < hot_min) clustered by their first out-neighbour, original order inside a
+    //          cluster: the row of that neighbour then gathers them as one sequential run of x]
+    //      ++ [nodes without explicit links: never gathered]
     g->new_of_old.alloc(n, &g->pool);
     g->old_of_new.alloc(n, &g->pool);
     g->relabelled = (g->opts.relabel == 0) && n > 1;
+    g->n_hot = n;
     if (g->relabelled) {
         DevBuf<u32> k0, k1, v0, v1;
         k0.alloc(n); k1.alloc(n); v0.alloc(n); v1.alloc(n);
@@ -403,6 +443,30 @@ static void graph_build_impl(rwr_graph* g) {
         bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, n, ceil_log2_u64((u64)hs.max_out + 1), st, &g->pool);
         k_invert_perm<<<grid_for(n), 256, 0, st>>>(fl ? v1.p : v0.p, n, g->old_of_new.p, g->new_of_old.p);
         KERNEL_CHECK();
+        const u32 hot_min = g->opts.hot_min_degree > 0 ? (u32)g->opts.hot_min_degree : 2u;
+        if (hot_min > 1) {
+            DevBuf<u32> counts, pos, total;
+            counts.alloc(2); pos.alloc(n); total.alloc(1);
+            CUDA_CHECK(cudaMemsetAsync(counts.p, 0, 2 * sizeof(u32), st));
+            k_cold_flags<<<grid_for(n), 256, 0, st>>>(g->row_ptr, n, hot_min, pos.p, counts.p);
+            KERNEL_CHECK();
+            prim::exclusive_scan<u32>(pos.p, pos.p, n, total.p, st, &g->pool);
+            u32 hc[2] = {0, 0}, n_cold = 0;
+            CUDA_CHECK(cudaMemcpyAsync(hc, counts.p, sizeof(hc), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(&n_cold, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            const u32 n_hot = hc[0];
+            g->n_hot = (int32_t)n_hot;
+            if (n_cold) {
+                DevBuf<u32> ck0, ck1, cv0, cv1;
+                ck0.alloc(n_cold); ck1.alloc(n_cold); cv0.alloc(n_cold); cv1.alloc(n_cold);
+                k_cold_keys<<<grid_for(n), 256, 0, st>>>(g->row_ptr, g->col, g->new_of_old.p, n, hot_min, n_hot, pos.p, ck0.p, cv0.p);
+                KERNEL_CHECK();
+                bool f2 = prim::radix_sort<u32>(ck0.p, ck1.p, cv0.p, cv1.p, n_cold, ceil_log2_u64((u64)n_hot + (u64)n + 1), st, &g->pool);
+                k_assign_cold<<<grid_for(n_cold), 256, 0, st>>>(f2 ? cv1.p : cv0.p, n_cold, n_hot, g->new_of_old.p, g->old_of_new.p);
+                KERNEL_CHECK();
+            }
+        }
         CUDA_CHECK(cudaStreamSynchronize(st));
     } else if (n) {
         k_identity_perm<<<grid_for(n), 256, 0, st>>>(n, g->old_of_new.p, g->new_of_old.p);
@@ -536,6 +600,7 @@ int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info) {
     info->n_dangling = g->n_dangling;
     info->layout = g->built ? g->layout : 0;
     info->relabelled = g->relabelled ? 1 : 0;
+    info->n_hot = g->n_hot;
     info->hub_entries_fp64 = g->built ? hub_entries_for(g, RWR_FP64) : 0;
     info->hub_entries_fp32 = g->built ? hub_entries_for(g, RWR_FP32) : 0;
     info->n_chunks = g->n_chunks;

@@ -6,10 +6,10 @@
 // Merge-path work item geometry of the SpMV (iterate.cu).  One chunk = CHUNK_ITEMS path items (rows + nnz),
 // so a chunk holds at most CHUNK_ITEMS non-zeros; with the <= 3 alignment slack of the int4 index loads its
 // span fits the CHUNK_SPAN-entry product buffer.
-constexpr int GROUP_THREADS = 256;
+constexpr int GROUP_THREADS = 128;
 constexpr int CHUNK_ROUNDS = 2;                                   // int4 index loads per thread per chunk
-constexpr int CHUNK_SPAN = GROUP_THREADS * 4 * CHUNK_ROUNDS;      // 2048
-constexpr int CHUNK_ITEMS = CHUNK_SPAN - 4;                       // 2044
+constexpr int CHUNK_SPAN = GROUP_THREADS * 4 * CHUNK_ROUNDS;      // 1024
+constexpr int CHUNK_ITEMS = CHUNK_SPAN - 4;                       // 1020
 constexpr int IDX_PAD = 8;                                        // ints of slack after the index array
 
 struct rwr_comm;
@@ -50,6 +50,7 @@ struct rwr_graph {
 
     // ---- internal labelling (descending out-degree) and the pull CSR of W^T in internal labels
     bool relabelled = false;
+    int32_t n_hot = 0;                  // labels [0, n_hot): degree-sorted hot nodes; beyond: clustered cold nodes
     DevBuf<int32_t> new_of_old, old_of_new;   // [n]
     int layout = RWR_LAYOUT_VALUED;
     DevBuf<u32> in_ptr;                 // [n+1]

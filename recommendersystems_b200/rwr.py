@@ -98,9 +98,11 @@ class SynthSpec(dict):
         return N.rwr_synth_spec(**{k: int(d[k]) for k in self.FIELDS})
 
 
-def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_width=0, stream=0) -> N.rwr_opts:
+def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_width=0, stream=0, kernel=0,
+          hot_min_degree=0) -> N.rwr_opts:
     return N.rwr_opts(device=int(device), layout=int(layout), relabel=0 if relabel else 1, hub_entries=int(hub_entries),
-                      batch_width=int(batch_width), reserved0=0, stream=int(stream))
+                      batch_width=int(batch_width), kernel=int(kernel), stream=int(stream),
+                      hot_min_degree=int(hot_min_degree), reserved1=0)
 
 
 class Graph:
