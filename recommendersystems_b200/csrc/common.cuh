@@ -98,6 +98,61 @@ struct DevBuf {
     operator T*() const { return p; }
 };
 
+// Per-handle cache of device scratch blocks: request-path workspaces are reused instead of going through
+// cudaMalloc / cudaFree (which synchronise the device) on every call.
+struct ScratchPool {
+    struct Block { void* p; size_t bytes; bool used; };
+    std::vector<Block> blocks;
+    DevPool* pool = nullptr;
+    void* get(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        int best = -1;
+        for (int i = 0; i < (int)blocks.size(); i++)
+            if (!blocks[i].used && blocks[i].bytes >= bytes && blocks[i].bytes <= 2 * bytes + 4096 &&
+                (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
+        if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
+        void* p = nullptr;
+        cudaError_t err = cudaMalloc(&p, bytes);
+        if (err != cudaSuccess) {            // drop every cached free block and retry once
+            cudaGetLastError();
+            trim();
+            err = cudaMalloc(&p, bytes);
+        }
+        if (err != cudaSuccess) {
+            rwr_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
+            throw RwrError{err == cudaErrorMemoryAllocation ? RWR_E_OOM : RWR_E_CUDA};
+        }
+        if (pool) pool->bytes += (int64_t)bytes;
+        blocks.push_back({p, bytes, true});
+        return p;
+    }
+    void put(void* p) {
+        for (auto& b : blocks) if (b.p == p) { b.used = false; return; }
+    }
+    void trim() {
+        std::vector<Block> keep;
+        for (auto& b : blocks) {
+            if (b.used) keep.push_back(b);
+            else { cudaFree(b.p); if (pool) pool->bytes -= (int64_t)b.bytes; }
+        }
+        blocks.swap(keep);
+    }
+    ~ScratchPool() { for (auto& b : blocks) cudaFree(b.p); }
+};
+
+template <typename T>
+struct Scratch {
+    T* p = nullptr;
+    ScratchPool* sp = nullptr;
+    Scratch() {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() { release(); }
+    void alloc(ScratchPool* pool_, size_t count) { release(); sp = pool_; p = (T*)sp->get((count ? count : 1) * sizeof(T)); }
+    void release() { if (p && sp) sp->put(p); p = nullptr; }
+    operator T*() const { return p; }
+};
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 static inline int ceil_log2_u64(u64 n) {
     int L = 0;
@@ -155,6 +210,18 @@ __device__ __forceinline__ float ld_stream(const float* ptr, u64 pol) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ptr), "l"(pol));
     return r;
+}
+__device__ __forceinline__ u32 ld_stream_u32(const u32* ptr, u64 pol) {
+    u32 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(ptr), "l"(pol));
+    return r;
+}
+// stores with an L2 eviction policy (streamed results must not push the gathered vector out of L2)
+__device__ __forceinline__ void st_policy(double* ptr, double v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_policy(float* ptr, float v, u64 pol) {
+    asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
 }
 // gathered, re-used data: keep in L1 and last to leave L2
 __device__ __forceinline__ double ld_keep(const double* ptr, u64 pol) {

@@ -281,6 +281,7 @@ void graph_init_device(rwr_graph* g, const rwr_opts* opts) {
     CUDA_CHECK(cudaGetDeviceProperties(&prop, g->device));
     if (prop.major < 10)
         RWR_FAIL(RWR_E_CUDA, "device %d is sm_%d%d; librwr_b200 is built for sm_100a only", g->device, prop.major, prop.minor);
+    g->scratch.pool = &g->pool;
     g->sm_count = prop.multiProcessorCount;
     g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
     if (g->opts.stream) {

@@ -20,6 +20,7 @@ struct rwr_graph {
     bool own_stream = false;
     rwr_opts opts{};
     DevPool pool;
+    ScratchPool scratch;    // reusable request-path workspaces
 
     int32_t n = 0;          // nodes
     int64_t e0 = 0;         // raw links

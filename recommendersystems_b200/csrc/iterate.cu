@@ -100,9 +100,11 @@ template <typename T, bool WRITE_Y, bool RESID>
 __device__ __forceinline__ void finalize_row(const IterParams<T>& p, int row, T y, T invr, double uni_add, double& accS,
                                              double& accR) {
     if (p.seed < 0) y = add_rn(y, (T)uni_add);
-    if (WRITE_Y) p.y[row] = y;
+    const u64 pol_first = policy_evict_first();
+    if (WRITE_Y) st_policy(p.y + row, y, pol_first);
     const T rw = mul_rn(p.omc, y);
-    p.x_next[row] = mul_rn(rw, invr);
+    // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
+    st_policy(p.x_next + row, mul_rn(rw, invr), row < p.n_hot ? policy_evict_last() : pol_first);
     accS += (invr == (T)0) ? (double)y : (double)sub_rn(y, rw);
     if (RESID) {
         const T rp = p.r_prev[row];
@@ -538,7 +540,7 @@ __device__ __forceinline__ void phased_load(const IterParams<T>& p, int2 c0, int
     }
     const int r = c0.x + gtid;
     t.rs = 0; t.re = 0; t.inv = (T)0;
-    if (r < p.n) { t.rs = p.in_ptr[r]; t.re = p.in_ptr[r + 1]; t.inv = p.inv[r]; }
+    if (r < p.n) { t.rs = ld_stream_u32(p.in_ptr + r, pol); t.re = ld_stream_u32(p.in_ptr + r + 1, pol); t.inv = ld_stream(p.inv + r, pol); }
 }
 
 template <typename T, bool VALUED, bool WRITE_Y, bool RESID, bool DEBUG>
@@ -684,7 +686,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 1) k_spmv_phased(const IterParams
             u32 rs, re;
             T invr;
             if (first) { rs = my_rs; re = my_re; invr = my_inv; first = false; }
-            else { rs = p.in_ptr[r]; re = p.in_ptr[r + 1]; invr = p.inv[r]; }
+            else { rs = ld_stream_u32(p.in_ptr + r, pol_stream); re = ld_stream_u32(p.in_ptr + r + 1, pol_stream); invr = ld_stream(p.inv + r, pol_stream); }
             const u32 s = rs > nnz0 ? rs : nnz0;
             u32 e = complete ? re : nnz1;
             if (e < s) e = s;
@@ -879,7 +881,7 @@ void iterate_prepare(rwr_graph* g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
-static void ensure_fp32(rwr_graph* g) {
+void ensure_fp32_arrays(rwr_graph* g) {
     cudaStream_t st = g->stream;
     if (!g->inv32.p) {
         g->inv32.alloc((size_t)g->n + 4, &g->pool);
@@ -940,9 +942,9 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool write_y,
 }
 
 struct RunWorkspace {
-    DevBuf<unsigned char> xa, xb, ya;
-    DevBuf<double> carry, head, slot_S, slot_R;
-    DevBuf<IterCtl> ctl;
+    Scratch<unsigned char> xa, xb, ya;
+    Scratch<double> carry, head, slot_S, slot_R;
+    Scratch<IterCtl> ctl;
 };
 
 // Runs one seed.  mode 0: fixed n_iter; mode 1: threshold.  Final rank lands in y_out (internal labels).
@@ -1031,23 +1033,23 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
                     double thr, int max_iter, int32_t* iters_out) {
     cudaStream_t st = g->stream;
     const size_t n = (size_t)g->n;
-    if (Prec<T>::id == RWR_FP32) ensure_fp32(g);
+    if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     const size_t ld = (n + 3) & ~(size_t)3;
     res->ld = ld;
     Prec<T>::ybuf(res).alloc(std::max<size_t>(1, ld * (size_t)n_seeds), nullptr);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.xa.alloc(vec_bytes); ws.xb.alloc(vec_bytes); ws.ya.alloc(vec_bytes);
+    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
     CUDA_CHECK(cudaMemsetAsync(ws.xa.p, 0, vec_bytes, st));
     CUDA_CHECK(cudaMemsetAsync(ws.xb.p, 0, vec_bytes, st));
-    ws.carry.alloc((size_t)g->n_chunks); ws.head.alloc((size_t)g->n_chunks);
+    ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
-    ws.slot_S.alloc(slots); ws.slot_R.alloc(slots);
+    ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     CUDA_CHECK(cudaMemsetAsync(ws.slot_S.p, 0, slots * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.slot_R.p, 0, slots * sizeof(double), st));
-    ws.ctl.alloc(1);
+    ws.ctl.alloc(&g->scratch, 1);
     CUDA_CHECK(cudaMemsetAsync(ws.ctl.p, 0, sizeof(IterCtl), st));
     cudaEvent_t ev0, ev1, evA, evB;
     CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
@@ -1075,20 +1077,20 @@ template <typename T>
 static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float* spmv_ms, float* fixup_ms) {
     cudaStream_t st = g->stream;
     const size_t n = (size_t)g->n;
-    if (Prec<T>::id == RWR_FP32) ensure_fp32(g);
+    if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.xa.alloc(vec_bytes); ws.xb.alloc(vec_bytes); ws.ya.alloc(vec_bytes);
+    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
     CUDA_CHECK(cudaMemsetAsync(ws.xa.p, 0, vec_bytes, st));
     CUDA_CHECK(cudaMemsetAsync(ws.xb.p, 0, vec_bytes, st));
-    ws.carry.alloc((size_t)g->n_chunks); ws.head.alloc((size_t)g->n_chunks);
+    ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
-    ws.slot_S.alloc(slots); ws.slot_R.alloc(slots);
+    ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     CUDA_CHECK(cudaMemsetAsync(ws.slot_S.p, 0, slots * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.slot_R.p, 0, slots * sizeof(double), st));
-    ws.ctl.alloc(1);
+    ws.ctl.alloc(&g->scratch, 1);
     int seed_int = 0;
     CUDA_CHECK(cudaMemcpyAsync(&seed_int, g->new_of_old.p + seed_orig, sizeof(int), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
@@ -1139,6 +1141,34 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     *fixup_ms = (float)(b / reps);
     g->pool.launches += 1 + 2 * (3 + reps);
 }
+
+// One fixed-iteration run of one seed into a caller-provided rank vector (internal labels); used by the fused
+// request path (rwr_recommend) so that no result object and no cudaMalloc / cudaFree sit on that path.
+template <typename T>
+void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches) {
+    cudaStream_t st = g->stream;
+    const size_t n = (size_t)g->n;
+    if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
+    RunWorkspace ws;
+    const size_t vec_bytes = (n + 8) * sizeof(T);
+    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, 16);
+    ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
+    const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
+    ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
+    ws.ctl.alloc(&g->scratch, 1);
+    cudaEvent_t ev0, ev1;
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev0, cudaEventDefault));
+    CUDA_CHECK(cudaEventCreateWithFlags(&ev1, cudaEventDefault));
+    const int64_t l0 = g->pool.launches;
+    int it = 0;
+    double rs = 0;
+    run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, iter_ms, ev0, ev1);
+    *launches += g->pool.launches - l0;
+    cudaEventDestroy(ev0);
+    cudaEventDestroy(ev1);
+}
+template void iterate_single_into<double>(rwr_graph*, int, double, int, double*, float*, int64_t*);
+template void iterate_single_into<float>(rwr_graph*, int, double, int, float*, float*, int64_t*);
 
 static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int mode, int32_t n_iter, double thr,
                      int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out) {
@@ -1214,8 +1244,8 @@ int rwr_scores(rwr_result* r, int32_t seed_slot, double* out_n) {
     CUDA_CHECK(cudaSetDevice(g->device));
     const int n = g->n;
     if (n == 0) return RWR_OK;
-    DevBuf<double> tmp;
-    tmp.alloc(n);
+    Scratch<double> tmp;
+    tmp.alloc(&g->scratch, n);
     if (r->precision == RWR_FP64)
         k_unpermute<double><<<div_up(n, 256), 256, 0, g->stream>>>(r->y64.p + (size_t)seed_slot * r->ld, g->new_of_old.p, n, tmp.p);
     else

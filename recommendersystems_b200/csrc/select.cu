@@ -88,8 +88,9 @@ __device__ void block_extract(Cand (&list)[TOPK_MAX], int k, Cand* out, Cand* sm
     }
 }
 
+// y is read with a stride of `ld` elements: ld == 1 for one rank vector, ld == B for a column of a row-major tile
 template <typename T>
-__global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict__ y, const u8* __restrict__ type_int,
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict__ y, int ld, const u8* __restrict__ type_int,
                                                             const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
                                                             int n, int k, Cand* __restrict__ block_out) {
     __shared__ Cand sm_best[TOPK_THREADS / 32];
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict_
         if (type_int[j] != RWR_NODE_ITEM) continue;
         if ((excl[j >> 5] >> (j & 31)) & 1u) continue;
         Cand c;
-        c.key = score_key((double)y[j]);
+        c.key = score_key((double)y[(size_t)j * ld]);
         c.idx = j;
         const Cand& worst = list[TOPK_MAX - 1];
         if (worst.idx >= 0 && c.key < worst.key) continue;       // cheap reject before touching the id
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict_
 
 template <typename T>
 __global__ void __launch_bounds__(TOPK_THREADS) k_topk_merge(const Cand* __restrict__ cands, int n_cands, int k,
-                                                             const T* __restrict__ y, int64_t* __restrict__ out_ids,
+                                                             const T* __restrict__ y, int ld, int64_t* __restrict__ out_ids,
                                                              double* __restrict__ out_scores, int* __restrict__ out_count) {
     __shared__ Cand sm_best[TOPK_THREADS / 32];
     __shared__ int sm_owner[TOPK_THREADS / 32 + 1];
@@ -132,7 +133,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k_topk_merge(const Cand* __restr
         for (int i = 0; i < k; i++) {
             if (result[i].idx < 0) break;
             out_ids[i] = result[i].id;
-            out_scores[i] = (double)y[result[i].idx];
+            out_scores[i] = (double)y[(size_t)result[i].idx * ld];
             cnt++;
         }
         *out_count = cnt;
@@ -150,6 +151,11 @@ __global__ void k_mark_excluded(const int32_t* __restrict__ raw_dst, const u8* _
             atomicOr(&excl[j >> 5], 1u << (j & 31));
         }
     }
+}
+
+__global__ void k_lookup(const int32_t* __restrict__ table, const int32_t* __restrict__ keys, int n, int32_t* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = table[keys[i]];
 }
 
 // ---- full ranking helpers
@@ -217,11 +223,11 @@ static void mark_excluded(rwr_graph* g, int seed, u32* excl, size_t words) {
 }
 
 template <typename T>
-static void topk_one(rwr_graph* g, const T* y, int seed, int k, u32* excl, size_t words, Cand* block_out, int grid,
+static void topk_one(rwr_graph* g, const T* y, int ld, int seed, int k, u32* excl, size_t words, Cand* block_out, int grid,
                      int64_t* d_ids, double* d_scores, int* d_count) {
     mark_excluded(g, seed, excl, words);
-    k_topk_scan<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, g->node_type_int.p, g->node_id_int.p, excl, g->n, k, block_out);
-    k_topk_merge<T><<<1, TOPK_THREADS, 0, g->stream>>>(block_out, grid * k, k, y, d_ids, d_scores, d_count);
+    k_topk_scan<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, ld, g->node_type_int.p, g->node_id_int.p, excl, g->n, k, block_out);
+    k_topk_merge<T><<<1, TOPK_THREADS, 0, g->stream>>>(block_out, grid * k, k, y, ld, d_ids, d_scores, d_count);
     KERNEL_CHECK();
     g->pool.launches += 2;
 }
@@ -311,21 +317,21 @@ int rwr_topk(rwr_result* r, int32_t k, int64_t* out_ids, double* out_scores, int
     }
     const size_t words = ((size_t)g->n + 31) / 32 + 1;
     const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up((size_t)std::max(g->n, 1), TOPK_THREADS)));
-    DevBuf<u32> excl;
-    DevBuf<Cand> block_out;
-    DevBuf<int64_t> d_ids;
-    DevBuf<double> d_sc;
-    DevBuf<int> d_cnt;
-    excl.alloc(words); block_out.alloc((size_t)grid * k);
-    d_ids.alloc((size_t)S * k); d_sc.alloc((size_t)S * k); d_cnt.alloc(S);
+    Scratch<u32> excl;
+    Scratch<Cand> block_out;
+    Scratch<int64_t> d_ids;
+    Scratch<double> d_sc;
+    Scratch<int> d_cnt;
+    excl.alloc(&g->scratch, words); block_out.alloc(&g->scratch, (size_t)grid * k);
+    d_ids.alloc(&g->scratch, (size_t)S * k); d_sc.alloc(&g->scratch, (size_t)S * k); d_cnt.alloc(&g->scratch, S);
     CUDA_CHECK(cudaMemsetAsync(d_ids.p, 0, (size_t)S * k * 8, st));
     CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)S * k * 8, st));
     for (int s = 0; s < S; s++) {
         if (r->precision == RWR_FP64)
-            topk_one<double>(g, r->y64.p + (size_t)s * r->ld, r->seeds[s], k, excl.p, words, block_out.p, grid,
+            topk_one<double>(g, r->y64.p + (size_t)s * r->ld, 1, r->seeds[s], k, excl.p, words, block_out.p, grid,
                              d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
         else
-            topk_one<float>(g, r->y32.p + (size_t)s * r->ld, r->seeds[s], k, excl.p, words, block_out.p, grid,
+            topk_one<float>(g, r->y32.p + (size_t)s * r->ld, 1, r->seeds[s], k, excl.p, words, block_out.p, grid,
                             d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
     }
     CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids.p, (size_t)S * k * 8, cudaMemcpyDeviceToHost, st));
@@ -350,28 +356,168 @@ int rwr_rank_all(rwr_result* r, int32_t seed_slot, int64_t* ids, double* scores,
     RWR_API_END
 }
 
-// n_seeds x Recommendation(seed, c, nIter, k).  Seeds are processed in tiles; ranks are not kept.
+}  // extern "C"
+
+// n_seeds x Recommendation(seed, c, nIter, k).  Seeds are processed in SpMM tiles of B columns (8 FP64 / 16 FP32):
+// one pass over the matrix serves B seeds; the ranks of a tile are dropped once its top-k lists are out.
+template <typename T>
+void spmm_run_tile(rwr_graph* g, const int* seeds_int, int n_active, double c, int n_iter, T* y_out, int64_t* launches);
+int spmm_tile_width(int precision);
+void ensure_fp32_arrays(rwr_graph* g);
+
+template <typename T>
+void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches);
+
+// seeds one by one through the single-column kernel (k <= 16): no result objects, scratch from the handle's pool
+template <typename T>
+static void recommend_singles(rwr_graph* g, const int32_t* seeds, int n_seeds, double c, int n_iter, int k, int64_t* out_ids,
+                              double* out_scores, int32_t* out_counts, rwr_run_info* info) {
+    cudaStream_t st = g->stream;
+    const size_t n = (size_t)g->n;
+    Scratch<T> y;
+    y.alloc(&g->scratch, n + 8);
+    const size_t words = (n + 31) / 32 + 1;
+    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
+    Scratch<u32> excl;
+    Scratch<Cand> block_out;
+    Scratch<int64_t> d_ids;
+    Scratch<double> d_sc;
+    Scratch<int> d_cnt;
+    excl.alloc(&g->scratch, words); block_out.alloc(&g->scratch, (size_t)grid * k);
+    d_ids.alloc(&g->scratch, (size_t)n_seeds * k); d_sc.alloc(&g->scratch, (size_t)n_seeds * k); d_cnt.alloc(&g->scratch, n_seeds);
+    CUDA_CHECK(cudaMemsetAsync(d_ids.p, 0, (size_t)n_seeds * k * 8, st));
+    CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)n_seeds * k * 8, st));
+    float it_ms = 0.f;
+    int64_t launches = 0;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, st));
+    for (int s = 0; s < n_seeds; s++) {
+        iterate_single_into<T>(g, seeds[s], c, n_iter, y.p, &it_ms, &launches);
+        topk_one<T>(g, y.p, 1, seeds[s], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
+        launches += 3;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_scores, d_sc.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_counts, d_cnt.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaEventRecord(e1, st));
+    CUDA_CHECK(cudaEventSynchronize(e1));
+    float tot = 0.f;
+    CUDA_CHECK(cudaEventElapsedTime(&tot, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (info) {
+        info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = sizeof(T) == 4 ? RWR_FP32 : RWR_FP64;
+        info->iterations = n_iter; info->residual = NAN; info->iterate_ms = it_ms; info->total_ms = tot;
+        info->kernel_launches = launches;
+    }
+}
+
+template <typename T>
+static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, double c, int n_iter, int k, int64_t* out_ids,
+                            double* out_scores, int32_t* out_counts, rwr_run_info* info) {
+    cudaStream_t st = g->stream;
+    const int B = spmm_tile_width(sizeof(T) == 4 ? RWR_FP32 : RWR_FP64);
+    const size_t n = (size_t)g->n;
+    if (sizeof(T) == 4) ensure_fp32_arrays(g);
+    // internal labels of all seeds in one go
+    std::vector<int32_t> n2o((size_t)n_seeds);
+    {
+        Scratch<int32_t> d_seeds, d_int;
+        d_seeds.alloc(&g->scratch, n_seeds); d_int.alloc(&g->scratch, n_seeds);
+        CUDA_CHECK(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, st));
+        k_lookup<<<div_up((size_t)n_seeds, 256), 256, 0, st>>>(g->new_of_old.p, d_seeds.p, n_seeds, d_int.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(n2o.data(), d_int.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    Scratch<T> y;
+    y.alloc(&g->scratch, n * B + 16);
+    const size_t words = (n + 31) / 32 + 1;
+    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
+    Scratch<u32> excl;
+    Scratch<Cand> block_out;
+    Scratch<int64_t> d_ids;
+    Scratch<double> d_sc;
+    Scratch<int> d_cnt;
+    excl.alloc(&g->scratch, words); block_out.alloc(&g->scratch, (size_t)grid * k);
+    d_ids.alloc(&g->scratch, (size_t)n_seeds * k); d_sc.alloc(&g->scratch, (size_t)n_seeds * k); d_cnt.alloc(&g->scratch, n_seeds);
+    CUDA_CHECK(cudaMemsetAsync(d_ids.p, 0, (size_t)n_seeds * k * 8, st));
+    CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)n_seeds * k * 8, st));
+    cudaEvent_t e0, e1, e2;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
+    int64_t launches = 0;
+    float it_ms = 0.f, tot_ms = 0.f;
+    for (int s0 = 0; s0 < n_seeds; s0 += B) {
+        const int cnt = std::min(B, n_seeds - s0);
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        spmm_run_tile<T>(g, n2o.data() + s0, cnt, c, n_iter, y.p, &launches);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        for (int j = 0; j < cnt; j++) {
+            topk_one<T>(g, y.p + j, B, seeds[s0 + j], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)(s0 + j) * k,
+                        d_sc.p + (size_t)(s0 + j) * k, d_cnt.p + s0 + j);
+            launches += 3;
+        }
+        CUDA_CHECK(cudaEventRecord(e2, st));
+        CUDA_CHECK(cudaEventSynchronize(e2));
+        float a = 0.f, b = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&a, e0, e1));
+        CUDA_CHECK(cudaEventElapsedTime(&b, e0, e2));
+        it_ms += a; tot_ms += b;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_scores, d_sc.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(out_counts, d_cnt.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    if (info) {
+        info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = sizeof(T) == 4 ? RWR_FP32 : RWR_FP64;
+        info->iterations = n_iter; info->residual = NAN; info->iterate_ms = it_ms; info->total_ms = tot_ms;
+        info->kernel_launches = launches;
+    }
+}
+
+extern "C" {
+
 int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int32_t n_iter, int32_t precision,
                   int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts, rwr_run_info* info) {
     RWR_API_BEGIN
     if (!g || !out_ids || !out_scores || !out_counts || (n_seeds && !seeds)) RWR_FAIL(RWR_E_INVALID, "NULL argument");
     if (k <= 0) RWR_FAIL(RWR_E_INVALID, "k must be positive");
+    if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    if (precision != RWR_FP64 && precision != RWR_FP32) RWR_FAIL(RWR_E_INVALID, "unknown precision %d", precision);
     if (info) memset(info, 0, sizeof(*info));
-    const int tile = std::max(1, g->opts.batch_width > 0 ? g->opts.batch_width : 8);
-    for (int s0 = 0; s0 < n_seeds; s0 += tile) {
-        const int cnt = std::min(tile, n_seeds - s0);
-        rwr_result* res = nullptr;
-        int rc = rwr_run_fixed(g, seeds + s0, cnt, c, n_iter, precision, &res);
-        if (rc != RWR_OK) return rc;
-        rc = rwr_topk(res, k, out_ids + (size_t)s0 * k, out_scores + (size_t)s0 * k, out_counts + s0);
-        if (info) {
-            info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = precision; info->iterations = n_iter;
-            info->residual = NAN; info->iterate_ms += res->iterate_ms; info->total_ms += res->total_ms;
-            info->kernel_launches += res->launches + 3 * cnt;
-        }
-        rwr_result_destroy(res);
-        if (rc != RWR_OK) return rc;
+    if (n_seeds == 0) return RWR_OK;
+    if (n_iter < 0) n_iter = 0;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    bool all_regular = true;
+    for (int s = 0; s < n_seeds; s++) {
+        if (seeds[s] < -1 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);
+        if (seeds[s] < 0) all_regular = false;
     }
+    if (k <= TOPK_MAX && all_regular && (n_seeds < 2 || g->opts.batch_width == 1)) {
+        if (precision == RWR_FP64) recommend_singles<double>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
+        else recommend_singles<float>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
+        return RWR_OK;
+    }
+    if (k > TOPK_MAX || !all_regular) {
+        // result-object path per seed (k > 16 needs the full ranking; seed -1 is the uniform constructor)
+        for (int s = 0; s < n_seeds; s++) {
+            rwr_result* res = nullptr;
+            int rc = rwr_run_fixed(g, seeds + s, 1, c, n_iter, precision, &res);
+            if (rc != RWR_OK) return rc;
+            rc = rwr_topk(res, k, out_ids + (size_t)s * k, out_scores + (size_t)s * k, out_counts + s);
+            if (info) {
+                info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = precision; info->iterations = n_iter;
+                info->residual = NAN; info->iterate_ms += res->iterate_ms; info->total_ms += res->total_ms;
+                info->kernel_launches += res->launches + 3;
+            }
+            rwr_result_destroy(res);
+            if (rc != RWR_OK) return rc;
+        }
+        return RWR_OK;
+    }
+    if (precision == RWR_FP64) recommend_tiles<double>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
+    else recommend_tiles<float>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
     return RWR_OK;
     RWR_API_END
 }

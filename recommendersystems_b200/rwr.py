@@ -322,6 +322,11 @@ class Recommender:
                        topN: Optional[int] = None) -> List[Tuple[int, float]]:
         """`dampingFactor` is the reference's C# float: it is widened to double here, as at Recommender.cs:16."""
         c = widen_float(dampingFactor)
+        if topN is not None and 0 < topN <= 16:
+            # fused request path: seed in, top-k (id, score) pairs out, nothing else crosses the boundary
+            ids, sc, cnt = self.RecommendationBatch([int(idxTargetUser)], dampingFactor, nIteration, int(topN))
+            m = int(cnt[0])
+            return list(zip(ids[0, :m].tolist(), sc[0, :m].tolist()))
         res = run_fixed(self.graph, [int(idxTargetUser)], c, int(nIteration), self.precision)
         try:
             self.last_info = res.info()

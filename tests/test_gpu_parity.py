@@ -404,3 +404,37 @@ def test_determinism_and_full_size_properties():
     assert_close_fp64(a, want, "22M-link graph")
     oids, osc = og.recommend(seed, 0.15, 20, top_n=10)
     same_ranking(tid[0, :tcnt[0]], tsc[0, :tcnt[0]], oids, osc)
+
+
+# ------------------------------------------------------------------------------------------ batched SpMM path (K8)
+@pytest.mark.parametrize("unit", [False, True])
+def test_batched_spmm_matches_oracle_and_single_column(unit):
+    """rwr_recommend in SpMM tiles (8 FP64 / 16 FP32 columns): hubs crossing tiles, partial last tile, both layouts."""
+    spec = dict(seed=9, n_users=6_000, n_items=50_000, n_third=1_000, authorship_per_mille=600, n_like=160_000,
+                n_friend=40_000, n_follow=5_000, n_mention=0 if unit else 1_500, undefined_per_mille=30, scramble=1, p1_byte=45)
+    cpu = O.synth_generate(spec)
+    og = oracle_graph(cpu)
+    gg = rs.Graph.synthetic(spec)
+    gg.buildGraph()
+    info = gg.info()
+    assert info.layout == (N.LAYOUT_INDEX if unit else N.LAYOUT_VALUED) and info.max_in_degree > 2 * 1020
+    raw_deg = np.bincount(cpu["src"], minlength=og.n)
+    users = np.flatnonzero(raw_deg[:spec["n_users"]] > 0)
+    seeds = [int(np.argmax(raw_deg))] + [int(u) for u in users[:: max(1, len(users) // 18)][:18]]      # 19 seeds: 3 FP64 tiles
+    rec = rs.Recommender(gg)
+    ids, sc, cnt = rec.RecommendationBatch(seeds, 0.15, 12, 10)
+    assert rec.last_info.kernel_launches > 0
+    for i, seed in enumerate(seeds):
+        oids, osc = og.recommend(seed, 0.15, 12, top_n=10)
+        same_ranking(ids[i, :cnt[i]], sc[i, :cnt[i]], oids, osc)
+        assert_close_fp64(sc[i, :cnt[i]], osc, f"batched seed {seed}")
+        single = rec.Recommendation(seed, 0.15, 12, 10)
+        assert [p[0] for p in single] == ids[i, :cnt[i]].tolist()
+    rec32 = rs.Recommender(gg, precision=rs.FP32)
+    ids32, sc32, cnt32 = rec32.RecommendationBatch(seeds, 0.15, 12, 10)
+    for i, seed in enumerate(seeds):
+        oids, osc = og.recommend(seed, 0.15, 12, top_n=10)
+        assert cnt32[i] == len(oids)
+        assert np.abs(sc32[i, :cnt32[i]] - osc).max() <= 2e-6 * max(osc.max(), 1e-30) + 1e-30
+    with pytest.raises(KeyError):
+        rec.RecommendationBatch([seeds[0], int(np.flatnonzero(raw_deg == 0)[0])], 0.15, 3, 5)
