@@ -196,12 +196,26 @@ def run_ours(args):
         last_top = rec.Recommendation(int(seeds[n_total + args.warmup + i]), C_FLOAT, N_ITER, TOP_K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # ---- C3 leg: batched seeds through the SpMM tiles (8 FP64 / 16 FP32 columns per matrix pass), seeds sharded
+    #      over the ranks with no communication; host seed list in, top-10 lists out
+    nb = args.batch_seeds
+    bseeds = pick_seeds(raw_deg, spec["n_users"], nb, offset=100_000 + rank * nb)
+    batched = {}
+    for bprec, bname in ((rs.FP64, "fp64"), (rs.FP32, "fp32")):
+        brec = rs.Recommender(g, bprec)
+        brec.RecommendationBatch(bseeds[:16], C_FLOAT, N_ITER, TOP_K)
+        barrier()
+        t0 = time.perf_counter()
+        brec.RecommendationBatch(bseeds, C_FLOAT, N_ITER, TOP_K)
+        torch.cuda.synchronize()
+        batched[bname] = (time.perf_counter() - t0, brec.last_info.iterate_ms * 1e-3)
     clocks = sampler.stop()
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, iter_ms], dtype=torch.float64, device="cuda")
+    times = torch.tensor([dev_ms, e2e_s * 1e3, iter_ms, batched["fp64"][0], batched["fp32"][0], batched["fp64"][1],
+                          batched["fp32"][1]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, iter_ms = (float(x) for x in times.tolist())
+    dev_ms, e2e_ms, iter_ms, b64_s, b32_s, b64_it, b32_it = (float(x) for x in times.tolist())
     edges_total = float(nnz) * N_ITER * args.steps * world
     value = edges_total / (dev_ms * 1e-3) / 1e9
     e2e_value = edges_total / (e2e_ms * 1e-3) / 1e9
@@ -249,7 +263,15 @@ def run_ours(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "GTEPS", "h2d_bytes_per_step": 4,
                     "d2h_bytes_per_step": TOP_K * 16 + 4, "ms_per_step": round(e2e_ms / args.steps, 4),
                     "seeds_per_s": round(args.steps * world / (e2e_ms * 1e-3), 2),
-                    "api": "Recommender.Recommendation(seed, 0.15f, 20, 10) -> rwr_run_fixed + rwr_topk"},
+                    "api": "Recommender.Recommendation(seed, 0.15f, 20, 10) -> rwr_recommend (C ABI)"},
+            "batched": {"workload": f"C3: {nb} seeds per GPU as SpMM tiles on the same graph, top-10 per seed, seeds "
+                                    f"sharded x{world} (no collective)",
+                        "fp64": {"seeds_per_s": round(nb * world / b64_s, 1),
+                                 "seed_gteps_e2e": round(nnz * N_ITER * nb * world / b64_s / 1e9, 1),
+                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * nb * world / b64_it / 1e9, 1)},
+                        "fp32": {"seeds_per_s": round(nb * world / b32_s, 1),
+                                 "seed_gteps_e2e": round(nnz * N_ITER * nb * world / b32_s / 1e9, 1),
+                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * nb * world / b32_it / 1e9, 1)}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -307,15 +329,17 @@ def run_reference(args):
     sample_iters = args.cpu_iters
     n_total = args.warmup + args.steps
     seeds = pick_seeds(raw_deg, spec["n_users"], n_total * threads)
+    # Model.run(n) only: the reference's full sort of ~10 M candidates (Recommender.cs:35) is left out of the sample,
+    # which favours the reference arm (our e2e figure includes top-k and the host copies)
     for i in range(args.warmup):
-        og.recommend_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, TOP_K, threads)
+        og.run_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, threads)
     t0 = time.perf_counter()
     for i in range(args.warmup, n_total):
-        og.recommend_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, TOP_K, threads)
+        og.run_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, threads)
     dt = time.perf_counter() - t0
     value = nnz * sample_iters * threads * args.steps / dt / 1e9
     sample = (f"each step = {threads} seeds on {threads} threads (one graph per thread, Program.cs:11/:61-66), "
-              f"{sample_iters} of 20 iterations + top-10 each, collapsed O(E+N) form, full graph")
+              f"Model.run({sample_iters}) each ({sample_iters} of 20 iterations, no ranking), collapsed O(E+N) form, full graph")
     line = {
         "impl": "reference",
         "metric": "RWR GTEPS (nnz x iterations x seeds / s), single-seed, 20 iterations",
@@ -345,6 +369,7 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("RWR_BENCH_SCALE", "1.0")))
     ap.add_argument("--cpu-iters", type=int, default=2, help="iterations of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--batch-seeds", type=int, default=64, help="seeds per GPU of the batched (C3) leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

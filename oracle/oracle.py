@@ -43,6 +43,7 @@ def lib() -> C.CDLL:
         L.orc_rank_scores.restype = i64
         L.orc_rank_scores.argtypes = [vp, i32, vp, vp, vp, i64]
         L.orc_recommend_many.argtypes = [vp, vp, i32, f64, i32, i32, i32, vp, vp, vp]
+        L.orc_run_many.argtypes = [vp, vp, i32, f64, i32, i32, vp]
         L.orc_evaluate.argtypes = [vp, i64, vp, i64, vp, vp]
         L.orc_synth_create.restype = vp
         L.orc_synth_create.argtypes = [vp]
@@ -180,6 +181,19 @@ class OracleGraph:
         if rc < 0:
             raise RuntimeError(f"orc_recommend_many rc={rc}")
         return ids, sc, cnt
+
+
+def _run_many(self, seeds, damping_float: float, n_iter: int, n_threads: int):
+    """Model.run(n_iter) for each seed, n_threads seeds in flight -> rank[seed] per seed."""
+    seeds = np.ascontiguousarray(seeds, np.int32)
+    chk = np.zeros(len(seeds), np.float64)
+    rc = lib().orc_run_many(self._h, _p(seeds), len(seeds), widen_float(damping_float), int(n_iter), int(n_threads), _p(chk))
+    if rc < 0:
+        raise RuntimeError(f"orc_run_many rc={rc}")
+    return chk
+
+
+OracleGraph.run_many = _run_many
 
 
 def evaluate(ids, test_ids):

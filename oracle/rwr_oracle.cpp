@@ -522,6 +522,27 @@ int orc_recommend_many(void* h, const int32_t* seeds, int32_t n_seeds, double da
     return ORC_OK;
 }
 
+// Model.run(n_iter) for several seeds at once, one thread per seed in flight (<= n_threads), collapsed form.
+// checksum[s] = rank[seed_s] so the work cannot be optimised away.
+int orc_run_many(void* h, const int32_t* seeds, int32_t n_seeds, double damping, int32_t n_iter, int32_t n_threads,
+                 double* checksum) {
+    OrcGraph* g = (OrcGraph*)h;
+    if (!g || !g->built) return ORC_E_NOT_BUILT;
+    if (n_threads < 1) n_threads = 1;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < n_threads; t++) {
+        pool.emplace_back([&, t]() {
+            for (int32_t s = t; s < n_seeds; s += n_threads) {
+                Model m(*g, damping, seeds[s], false);
+                m.run_fixed(n_iter);
+                checksum[s] = (seeds[s] >= 0 && seeds[s] < g->n) ? m.rank[seeds[s]] : 0.0;
+            }
+        });
+    }
+    for (auto& th : pool) th.join();
+    return ORC_OK;
+}
+
 // Experiment.cs:121-128; `test` must be sorted ascending (HashSet<long>.Contains as a binary search)
 void orc_evaluate(const int64_t* ids, int64_t n, const int64_t* test_sorted, int64_t n_test, int32_t* hits, double* avg_precision) {
     int nHits = 0;
