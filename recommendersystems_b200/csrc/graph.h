@@ -62,6 +62,13 @@ struct rwr_graph {
     DevBuf<float> inv32;
     DevBuf<int2> part;                  // [n_chunks + 1] merge-path start coordinates (row, nnz)
     int32_t n_chunks = 0;
+    // ---- edge stream of the warp-streamed SpMV (stream.cu)
+    DevBuf<int32_t> ws_src;             // [ws_tiles * WS_TILE] source label | bit 31 on the last link of a row
+    DevBuf<double> ws_val64;            // valued layout
+    DevBuf<float> ws_val32;             // lazily built for FP32 runs
+    DevBuf<u32> ws_tile;                // [ws_tiles + 1]
+    int32_t ws_tiles = 0;
+    int64_t ws_nnz = 0;                 // nnz + one padding link per row without in-links
     DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
     DevBuf<u8> node_type_int;
     DevBuf<int32_t> items_by_id_desc;   // lazily: internal indices of ITEM nodes, id descending (full ranking)

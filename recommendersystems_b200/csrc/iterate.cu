@@ -21,111 +21,9 @@
 
 #include "iterate.h"
 
-constexpr int GROUPS = 8;
-constexpr int CTA_THREADS = GROUPS * GROUP_THREADS;       // 1024
-constexpr int LONG_ROW = 64;                              // rows with >= LONG_ROW nnz inside a chunk: one warp
-constexpr int LONG_CAP = CHUNK_ITEMS / LONG_ROW + 1;      // 16
-constexpr int FIX_THREADS = 256;
+#include "iterate_dev.cuh"
+#include "stream.h"
 
-template <typename T>
-struct IterParams {
-    const u32* in_ptr;
-    const int32_t* in_src;
-    const T* in_val;        // valued layout only
-    const int2* part;
-    int n_chunks;
-    int n;
-    const T* x;             // gather source, internal labels
-    const T* inv;
-    const T* r_prev;        // previous rank (residual)
-    T* y;
-    T* x_next;
-    T omc;                  // (1 - c)
-    int seed;               // internal label, -1: uniform restart
-    double inv_n;           // 1/N (uniform restart)
-    int hub;                // x entries staged in shared memory
-    int n_hot;              // labels below: hot, L2-resident (evict-last); above: clustered cold nodes (streamed)
-    int debug;              // measurement-only ablations of the phased kernel (RWR_DEBUG_MODE, profile hook only)
-    double* head_partial;   // [n_chunks] row sums are accumulated in double in both precisions
-    double* carry;          // [n_chunks]
-    double* slot_S;         // [main_grid + fix_grid]
-    double* slot_R;
-    IterCtl* ctl;
-};
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void group_sync(int group) {
-    asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "r"(GROUP_THREADS) : "memory");
-}
-__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// TMA 1-D bulk copy global -> shared, completion on an mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src, u32 bytes, u64* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-__device__ __forceinline__ void load4_stream(const double* p, u64 pol, double out[4]) {
-    out[0] = ld_stream(p, pol); out[1] = ld_stream(p + 1, pol); out[2] = ld_stream(p + 2, pol); out[3] = ld_stream(p + 3, pol);
-}
-__device__ __forceinline__ void load4_stream(const float* p, u64 pol, float out[4]) {
-    out[0] = ld_stream(p, pol); out[1] = ld_stream(p + 1, pol); out[2] = ld_stream(p + 2, pol); out[3] = ld_stream(p + 3, pol);
-}
-
-// ------------------------------------------------------------------------------------------------ epilogue
-// One finished row t with pull sum y (Model.cs:84, :91, :96-97 folded into per-row form):
-//   next x_t = fl(fl((1-c) y) * inv_t);  restart mass += inv_t == 0 ? y : y - fl((1-c) y);  residual += |r_t - y|
-template <typename T, bool WRITE_Y, bool RESID>
-__device__ __forceinline__ void finalize_row(const IterParams<T>& p, int row, T y, T invr, double uni_add, double& accS,
-                                             double& accR) {
-    if (p.seed < 0) y = add_rn(y, (T)uni_add);
-    const u64 pol_first = policy_evict_first();
-    if (WRITE_Y) st_policy(p.y + row, y, pol_first);
-    const T rw = mul_rn(p.omc, y);
-    // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
-    st_policy(p.x_next + row, mul_rn(rw, invr), row < p.n_hot ? policy_evict_last() : pol_first);
-    accS += (invr == (T)0) ? (double)y : (double)sub_rn(y, rw);
-    if (RESID) {
-        const T rp = p.r_prev[row];
-        accR += (double)((rp > y) ? sub_rn(rp, y) : sub_rn(y, rp));
-    }
-}
-
-// fixed-order block reduction of two doubles; result valid in thread 0
-template <int THREADS>
-__device__ __forceinline__ void block_sum2(double& a, double& b, double* scratch /* 2 * THREADS/32 */) {
-    a = warp_sum(a);
-    b = warp_sum(b);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { scratch[warp] = a; scratch[THREADS / 32 + warp] = b; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double sa = 0, sb = 0;
-        for (int w = 0; w < THREADS / 32; w++) { sa += scratch[w]; sb += scratch[THREADS / 32 + w]; }
-        a = sa; b = sb;
-    }
-}
 
 // ------------------------------------------------------------------------------------------------ K7 (variant): pipelined SpMV, rwr_opts.kernel = 1
 // Warp-specialised: per CTA 2 producer groups and 2 consumer groups of 256 threads, paired through a ring of
@@ -156,74 +54,6 @@ template <typename T> struct StageOff {
     static constexpr u32 size = coord + 16;
 };
 static_assert(StageOff<double>::size == sizeof(Stage<double>) && StageOff<float>::size == sizeof(Stage<float>), "stage layout");
-
-__device__ __forceinline__ void mbar_arrive_a(u32 bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_a(u32 bar, u32 parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(bar),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ double lds_t(u32 a, double) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a)); return v; }
-__device__ __forceinline__ float lds_t(u32 a, float) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
-__device__ __forceinline__ u32 lds_u32(u32 a) { u32 v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ int4 lds_int4(u32 a) {
-    int4 v;
-    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
-    return v;
-}
-__device__ __forceinline__ void sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts_int4(u32 a, int4 v) {
-    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void sts_t(u32 a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void sts_t(u32 a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
-__device__ __forceinline__ void sts4(u32 a, const double (&v)[4]) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v[0]), "d"(v[1]) : "memory");
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(v[2]), "d"(v[3]) : "memory");
-}
-__device__ __forceinline__ void sts4(u32 a, const float (&v)[4]) {
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
-}
-
-// One gather, branch-free: hub hit -> ld.shared, miss -> ld.global (evict-last), out of range -> 0.  Divergent
-// branches here made ptxas re-wait on the gathers' scoreboard slot before every index compare, which serialised the
-// 8 gathers of a thread; predicated straight-line code lets all of them issue back to back.
-__device__ __forceinline__ double gather_sel(int take_hub, int take_glob, u32 saddr, const double* gaddr, u64 pol) {
-    double v;
-    asm volatile(
-        "{\n\t.reg .pred ph, pg;\n\t"
-        "setp.ne.b32 ph, %1, 0;\n\t"
-        "setp.ne.b32 pg, %2, 0;\n\t"
-        "mov.f64 %0, 0d0000000000000000;\n\t"
-        "@ph ld.shared.f64 %0, [%3];\n\t"
-        "@pg ld.global.nc.L2::cache_hint.f64 %0, [%4], %5;\n\t}"
-        : "=d"(v)
-        : "r"(take_hub), "r"(take_glob), "r"(saddr), "l"(gaddr), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ float gather_sel(int take_hub, int take_glob, u32 saddr, const float* gaddr, u64 pol) {
-    float v;
-    asm volatile(
-        "{\n\t.reg .pred ph, pg;\n\t"
-        "setp.ne.b32 ph, %1, 0;\n\t"
-        "setp.ne.b32 pg, %2, 0;\n\t"
-        "mov.f32 %0, 0f00000000;\n\t"
-        "@ph ld.shared.f32 %0, [%3];\n\t"
-        "@pg ld.global.nc.L2::cache_hint.f32 %0, [%4], %5;\n\t}"
-        : "=f"(v)
-        : "r"(take_hub), "r"(take_glob), "r"(saddr), "l"(gaddr), "l"(pol));
-    return v;
-}
 
 // sum of prod[q0 .. q1) in storage order; the shared loads are issued 8 at a time (adding +0.0 is exact)
 template <typename T>
@@ -816,8 +646,9 @@ __global__ void __launch_bounds__(FIX_THREADS) k_fixup(const IterParams<T> p, in
 // ------------------------------------------------------------------------------------------------ K6: init
 template <typename T>
 __global__ void k_init(int n, int seed, T omc, const T* __restrict__ inv, T* __restrict__ r0, T* __restrict__ x0,
-                       IterCtl* ctl, double S_uniform) {
+                       T* __restrict__ x1, IterCtl* ctl, double S_uniform) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 8) { x0[n + j] = (T)0; x1[n + j] = (T)0; }     // x[n] is the always-zero entry the edge stream pads with
     if (j == 0) {
         ctl->resid = 0.0; ctl->seed_sum = 0.0; ctl->seed_flag = 0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0;
         if (seed < 0) ctl->S = S_uniform;
@@ -862,6 +693,7 @@ static size_t smem_fixed_bytes(size_t elt) {     // the v1 kernel needs a little
 }
 
 int hub_entries_for(const rwr_graph* g, int precision) {
+    if (g->opts.kernel == 0) return ws_hub_entries(g, precision);
     const size_t elt = precision == RWR_FP32 ? 4 : 8;
     const size_t fixed = smem_fixed_bytes(elt);
     if ((size_t)g->max_smem_optin <= fixed) return 0;
@@ -879,6 +711,7 @@ void iterate_prepare(rwr_graph* g) {
     k_partition<<<div_up((size_t)g->n_chunks + 1, 256), 256, 0, st>>>(g->in_ptr.p, g->n, (u32)g->nnz, g->n_chunks, g->part.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
+    stream_prepare(g);
 }
 
 void ensure_fp32_arrays(rwr_graph* g) {
@@ -893,23 +726,30 @@ void ensure_fp32_arrays(rwr_graph* g) {
         if (g->nnz) k_f64_to_f32<<<div_up((size_t)g->nnz, 256), 256, 0, st>>>(g->in_val64.p, g->in_val32.p, (size_t)g->nnz);
         KERNEL_CHECK();
     }
+    if (g->layout == RWR_LAYOUT_VALUED && !g->ws_val32.p && g->ws_val64.n) {
+        g->ws_val32.alloc(g->ws_val64.n, &g->pool);
+        k_f64_to_f32<<<div_up(g->ws_val64.n, 256), 256, 0, st>>>(g->ws_val64.p, g->ws_val32.p, g->ws_val64.n);
+        KERNEL_CHECK();
+    }
 }
 
 template <typename T> struct Prec;
 template <> struct Prec<double> {
     static const double* inv(rwr_graph* g) { return g->inv64.p; }
     static const double* val(rwr_graph* g) { return g->in_val64.p; }
+    static const double* wsval(rwr_graph* g) { return g->ws_val64.p; }
     static DevBuf<double>& ybuf(rwr_result* r) { return r->y64; }
     static constexpr int id = RWR_FP64;
 };
 template <> struct Prec<float> {
     static const float* inv(rwr_graph* g) { return g->inv32.p; }
     static const float* val(rwr_graph* g) { return g->in_val32.p; }
+    static const float* wsval(rwr_graph* g) { return g->ws_val32.p; }
     static DevBuf<float>& ybuf(rwr_result* r) { return r->y32; }
     static constexpr int id = RWR_FP32;
 };
 
-// variant 0: the phased kernel (default); 1: the pipelined producer/consumer kernel (rwr_opts.kernel, A/B runs)
+// rwr_opts.kernel: 0 = the warp-streamed kernel of stream.cu (default); 1 = pipelined producer/consumer; 2 = phased
 template <typename T, bool VALUED, bool WRITE_Y, bool RESID>
 static void launch_spmv(const IterParams<T>& p, int variant, int grid, size_t smem, cudaStream_t st) {
     auto kern = variant != 1 ? (p.debug ? k_spmv_phased<T, VALUED, WRITE_Y, RESID, true> : k_spmv_phased<T, VALUED, WRITE_Y, RESID, false>)
@@ -923,6 +763,7 @@ template <typename T>
 static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool write_y, bool resid, int main_grid, int fix_grid,
                              size_t smem, double thr, int use_thr) {
     cudaStream_t st = g->stream;
+    if (g->opts.kernel == 0) { ws_launch_iteration<T>(g, p, resid, thr, use_thr); return; }
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
 #define LAUNCH(V, W, R)                                                                  \
     do {                                                                                 \
@@ -970,6 +811,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     IterParams<T> p;
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
     p.n_chunks = g->n_chunks; p.n = n; p.inv = Prec<T>::inv(g);
+    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
     p.omc = (T)(1.0 - c);                                      // Model.cs:84 `(1 - dampingFactor)`
     p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot; p.debug = 0;
     p.head_partial = ws.head.p; p.carry = ws.carry.p;
@@ -980,7 +822,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     const double S_uniform = (double)g->n_dangling + (double)(n - g->n_dangling) * (1.0 - omc_d);
     // r0 goes to y_out in fixed mode (also the answer for n_iter == 0); threshold mode ping-pongs ya <-> y_out
     T* r_cur = (mode == 0) ? y_out : ya;
-    k_init<T><<<div_up(std::max(n, 1), 256), 256, 0, st>>>(n, seed_int, p.omc, p.inv, r_cur, xa, ws.ctl.p, S_uniform);
+    k_init<T><<<div_up(std::max(n, 1), 256), 256, 0, st>>>(n, seed_int, p.omc, p.inv, r_cur, xa, xb, ws.ctl.p, S_uniform);
     KERNEL_CHECK();
     g->pool.launches += 1;
 
@@ -1045,7 +887,7 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
-    const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
+    const size_t slots = (size_t)g->sm_count * 8 + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     CUDA_CHECK(cudaMemsetAsync(ws.slot_S.p, 0, slots * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.slot_R.p, 0, slots * sizeof(double), st));
@@ -1086,7 +928,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
-    const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
+    const size_t slots = (size_t)g->sm_count * 8 + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     CUDA_CHECK(cudaMemsetAsync(ws.slot_S.p, 0, slots * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.slot_R.p, 0, slots * sizeof(double), st));
@@ -1105,11 +947,12 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     IterParams<T> p;
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
     p.n_chunks = g->n_chunks; p.n = g->n; p.inv = Prec<T>::inv(g);
+    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
     p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot;
     p.head_partial = ws.head.p; p.carry = ws.carry.p; p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
     p.r_prev = nullptr; p.y = ya;
     { const char* dm = getenv("RWR_DEBUG_MODE"); p.debug = dm ? atoi(dm) : 0; }
-    k_init<T><<<div_up(std::max((int)n, 1), 256), 256, 0, st>>>((int)n, seed_int, p.omc, p.inv, ya, xa, ws.ctl.p, 0.0);
+    k_init<T><<<div_up(std::max((int)n, 1), 256), 256, 0, st>>>((int)n, seed_int, p.omc, p.inv, ya, xa, xb, ws.ctl.p, 0.0);
     KERNEL_CHECK();
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     std::vector<cudaEvent_t> ev(3 * (size_t)reps);
@@ -1120,10 +963,12 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
         p.x = x_cur; p.x_next = x_nxt;
         const int r = it - 3;
         if (r >= 0) CUDA_CHECK(cudaEventRecord(ev[3 * r], st));
-        if (valued) launch_spmv<T, true, false, false>(p, g->opts.kernel, main_grid, smem, st);
+        if (g->opts.kernel == 0) ws_launch_spmv_only<T>(g, p);
+        else if (valued) launch_spmv<T, true, false, false>(p, g->opts.kernel, main_grid, smem, st);
         else launch_spmv<T, false, false, false>(p, g->opts.kernel, main_grid, smem, st);
         if (r >= 0) CUDA_CHECK(cudaEventRecord(ev[3 * r + 1], st));
-        k_fixup<T, false, false><<<fix_grid, FIX_THREADS, 0, st>>>(p, main_grid, 0.0, 0);
+        if (g->opts.kernel == 0) ws_launch_finish_only<T>(g, p, false, 0.0, 0);
+        else k_fixup<T, false, false><<<fix_grid, FIX_THREADS, 0, st>>>(p, main_grid, 0.0, 0);
         KERNEL_CHECK();
         if (r >= 0) CUDA_CHECK(cudaEventRecord(ev[3 * r + 2], st));
         std::swap(x_cur, x_nxt);
@@ -1153,7 +998,7 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     const size_t vec_bytes = (n + 8) * sizeof(T);
     ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, 16);
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
-    const size_t slots = (size_t)g->sm_count + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
+    const size_t slots = (size_t)g->sm_count * 8 + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     ws.ctl.alloc(&g->scratch, 1);
     cudaEvent_t ev0, ev1;

@@ -1,0 +1,511 @@
+// stream.cu -- K7 (default, rwr_opts.kernel = 0): warp-streamed SpMV over a flagged edge stream.
+//
+// Restates the push loop of Recommenders/RWRBased/Model.cs:76-100 as a pull over W^T, like iterate.cu, but with a
+// layout and a schedule built around what bounds this kernel on a B200: not HBM bytes but the ~1 scattered gather per
+// cycle per SM the L1TEX path sustains (profiles/microbench/gather_bench.cu: 289 G reads/s from L2, 1500 G reads/s
+// from shared memory).  Everything else is arranged so that the gather queue never runs dry.
+//
+// Layout ("edge stream", built once per graph by stream_prepare):
+//   ws_src[q]   source label of the q-th stored link of W^T, rows back to back; bit 31 set on the LAST link of a row.
+//               A row without in-links gets one padding link to the always-zero entry x[n], so every row owns >= 1
+//               link, row ids are implicit (count the end flags) and y / x_next of such rows are written like any other.
+//   ws_val[q]   normalised weight of the link (valued layout only; the index-only layout folds the row's common
+//               weight into x, see graph.cu)
+//   ws_tile[t]  row of the first link of tile t (WS_TILE links) | bit 31 when that row started in an earlier tile
+//
+// Schedule: 16 independent warps per SM, no block-level barrier inside the loop.  A warp walks tiles t = w, w + W, ...
+// in steps of 128 links (one int4 of indices per lane, coalesced, evict-first).  Indices are loaded two steps ahead
+// and the gathers of x are issued one step ahead (branch-free: shared-memory hub table for the hottest sources, L2
+// otherwise), so ~4 k gathers per SM are always in flight.  Row sums: a step without a row end just adds into a
+// per-lane accumulator; a step with row ends runs a warp-level segmented scan (shuffles only), and the lanes holding
+// a row end run the fused epilogue (y, next x, restart mass, L1 residual).  The open row at a tile boundary goes to
+// tail[t] / head[t] and is closed by k_fixup_ws in a fixed order -- no floating-point atomics anywhere, so a run is
+// bit-reproducible; the association of a row sum differs from the reference's sequential one by O(log deg) ulp.
+#include <algorithm>
+#include <cmath>
+
+#include "iterate_dev.cuh"
+#include "primitives.cuh"
+#include "stream.h"
+
+constexpr u32 END_BIT = 0x80000000u;
+
+#ifdef RWR_PROFILE_CLOCKS
+__device__ unsigned long long g_clk_ws[16];
+#define WCLK_DECL long long wclk0 = clock64(), wclk1; unsigned long long wclk[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define WCLK(slot) do { wclk1 = clock64(); wclk[slot] += (unsigned long long)(wclk1 - wclk0); wclk0 = wclk1; } while (0)
+#define WCLK_FLUSH do { if (lane == 0) for (int i = 0; i < 8; i++) atomicAdd(&g_clk_ws[i], wclk[i]); } while (0)
+#else
+#define WCLK_DECL
+#define WCLK(slot)
+#define WCLK_FLUSH
+#endif
+
+// ------------------------------------------------------------------------------------------------ layout build
+__global__ void k_ws_len(const u32* __restrict__ in_ptr, int n, u32* __restrict__ len) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n) {
+        const u32 d = in_ptr[r + 1] - in_ptr[r];
+        len[r] = d ? d : 1u;
+    }
+}
+
+// largest r in [0, n) with ptr2[r] <= q   (ptr2 strictly increasing: every row owns >= 1 link)
+__device__ __forceinline__ int ws_row_of(const u32* __restrict__ ptr2, int n, u32 q) {
+    int lo = 0, hi = n;                       // invariant: ptr2[lo] <= q < ptr2[hi]  (ptr2[n] = total > q)
+    while (hi - lo > 1) {
+        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+        if (ptr2[mid] <= q) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
+                          const double* __restrict__ in_val, int n, u32 nnz2, size_t padded, int32_t* __restrict__ ws_src,
+                          double* __restrict__ ws_val /* may be null */) {
+    const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phys >= padded) return;
+    // Inside a stage of WS_STAGE links the stream is stored lane-major: the int4 that lane L loads in round j (physical
+    // offset j*128 + L*4) holds the links L*8 + j*4 .. +3 of the stage, so a lane owns 8 consecutive links.
+    const u32 o = (u32)(phys % WS_STAGE);
+    const u32 rnd = o / WS_STEP, ln = (o % WS_STEP) / 4, k = o % 4;
+    const size_t q = phys - o + (size_t)(ln * (WS_R * 4) + rnd * 4 + k);
+    if (q >= nnz2) {                          // tail padding of the last tile: zero entry, no flag
+        ws_src[phys] = n;
+        if (ws_val) ws_val[phys] = 0.0;
+        return;
+    }
+    const int r = ws_row_of(ptr2, n, (u32)q);
+    const u32 j = (u32)q - ptr2[r];
+    const u32 b = in_ptr[r], deg = in_ptr[r + 1] - b;
+    if (deg == 0) {
+        ws_src[phys] = (int32_t)((u32)n | END_BIT);
+        if (ws_val) ws_val[phys] = 0.0;
+    } else {
+        ws_src[phys] = (int32_t)((u32)in_src[b + j] | (j == deg - 1 ? END_BIT : 0u));
+        if (ws_val) ws_val[phys] = in_val[b + j];
+    }
+}
+
+__global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, int n_tiles, u32* __restrict__ ws_tile) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { ws_tile[t] = (u32)n; return; }
+    const u32 q = (u32)t * (u32)WS_TILE;
+    const int r = ws_row_of(ptr2, n, q);
+    ws_tile[t] = (u32)r | (q > ptr2[r] ? END_BIT : 0u);
+}
+
+void stream_prepare(rwr_graph* g) {
+    cudaStream_t st = g->stream;
+    const int n = g->n;
+    g->ws_tiles = 0;
+    g->ws_nnz = 0;
+    if (n == 0) {
+        g->ws_tile.alloc(1, &g->pool);
+        CUDA_CHECK(cudaMemsetAsync(g->ws_tile.p, 0, sizeof(u32), st));
+        return;
+    }
+    const u64 nnz2_max = (u64)g->nnz + (u64)n;
+    if (nnz2_max + WS_TILE >= (1ull << 32)) RWR_FAIL(RWR_E_UNSUPPORTED, "edge stream of %llu links exceeds 32-bit offsets", (unsigned long long)nnz2_max);
+    DevBuf<u32> ptr2, total;
+    ptr2.alloc((size_t)n + 1);
+    total.alloc(1);
+    k_ws_len<<<div_up(n, 256), 256, 0, st>>>(g->in_ptr.p, n, ptr2.p);
+    KERNEL_CHECK();
+    prim::exclusive_scan<u32>(ptr2.p, ptr2.p, n, total.p, st, &g->pool);
+    u32 nnz2 = 0;
+    CUDA_CHECK(cudaMemcpyAsync(&nnz2, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(ptr2.p + n, total.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    const int n_tiles = (int)(((u64)nnz2 + WS_TILE - 1) / WS_TILE);
+    const size_t padded = (size_t)n_tiles * WS_TILE;
+    g->ws_nnz = nnz2;
+    g->ws_tiles = n_tiles;
+    g->ws_src.alloc(padded, &g->pool);
+    const bool valued = g->layout == RWR_LAYOUT_VALUED;
+    if (valued) g->ws_val64.alloc(padded, &g->pool);
+    g->ws_tile.alloc((size_t)n_tiles + 1, &g->pool);
+    k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, nnz2,
+                                                  padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, n_tiles, g->ws_tile.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+int ws_hub_entries(const rwr_graph* g, int precision) {
+    const size_t elt = precision == RWR_FP32 ? 4 : 8;
+    if ((size_t)g->max_smem_optin <= (size_t)WS_HDR) return 0;
+    long cap = (long)(((size_t)g->max_smem_optin - WS_HDR) / elt) & ~3L;
+    long want = g->opts.hub_entries < 0 ? cap : std::min<long>(cap, (long)g->opts.hub_entries & ~3L);
+    long n4 = ((long)g->n + 3) & ~3L;
+    return (int)std::max<long>(0, std::min(want, n4));
+}
+
+// ------------------------------------------------------------------------------------------------ the kernel
+// Gathers of one stage (WS_R int4 of sources per lane).  One generic-address load per link: the address points either
+// into the CTA's shared-memory hub table (hot sources) or at x in global memory (L2).  One instruction and one
+// destination register per link, no branch, nothing for a later load to wait on.
+#ifndef WS_GATHER_GENERIC
+#define WS_GATHER_GENERIC 1
+#endif
+__device__ __forceinline__ void ws_ld_generic(double& v, u64 a) { asm volatile("ld.f64 %0, [%1];" : "=d"(v) : "l"(a)); }
+__device__ __forceinline__ void ws_ld_generic(float& v, u64 a) { asm volatile("ld.f32 %0, [%1];" : "=f"(v) : "l"(a)); }
+__device__ __forceinline__ void ws_lds_if(double& v, int s, int hub, u32 addr) {
+    asm volatile("{\n\t.reg .pred ph;\n\tsetp.lt.s32 ph, %1, %2;\n\t@ph ld.shared.f64 %0, [%3];\n\t}" : "=d"(v) : "r"(s), "r"(hub), "r"(addr));
+}
+__device__ __forceinline__ void ws_lds_if(float& v, int s, int hub, u32 addr) {
+    asm volatile("{\n\t.reg .pred ph;\n\tsetp.lt.s32 ph, %1, %2;\n\t@ph ld.shared.f32 %0, [%3];\n\t}" : "=f"(v) : "r"(s), "r"(hub), "r"(addr));
+}
+__device__ __forceinline__ void ws_ldg_if(double& v, int s, int hub, const double* addr, u64 pol) {
+    asm volatile("{\n\t.reg .pred pg;\n\tsetp.ge.s32 pg, %1, %2;\n\t@pg ld.global.nc.L2::cache_hint.f64 %0, [%3], %4;\n\t}"
+                 : "+d"(v) : "r"(s), "r"(hub), "l"(addr), "l"(pol));
+}
+__device__ __forceinline__ void ws_ldg_if(float& v, int s, int hub, const float* addr, u64 pol) {
+    asm volatile("{\n\t.reg .pred pg;\n\tsetp.ge.s32 pg, %1, %2;\n\t@pg ld.global.nc.L2::cache_hint.f32 %0, [%3], %4;\n\t}"
+                 : "+f"(v) : "r"(s), "r"(hub), "l"(addr), "l"(pol));
+}
+
+template <typename T>
+__device__ __forceinline__ void ws_gather_stage(const IterParams<T>& p, const int4 (&iv)[WS_R], u64 hub_gen, u32 hub_addr,
+                                                u64 pol_keep, u64 pol_stream, T (&v)[WS_R][4]) {
+    int s[WS_R][4];
+#pragma unroll
+    for (int j = 0; j < WS_R; j++) {
+        s[j][0] = iv[j].x & 0x7fffffff; s[j][1] = iv[j].y & 0x7fffffff; s[j][2] = iv[j].z & 0x7fffffff; s[j][3] = iv[j].w & 0x7fffffff;
+    }
+#if WS_GATHER_GENERIC
+    const u64 xg = (u64)(uintptr_t)p.x;
+#pragma unroll
+    for (int j = 0; j < WS_R; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            ws_ld_generic(v[j][k], (s[j][k] < p.hub ? hub_gen : xg) + (u64)(u32)s[j][k] * sizeof(T));
+#else
+#pragma unroll
+    for (int j = 0; j < WS_R; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) ws_lds_if(v[j][k], s[j][k], p.hub, hub_addr + (u32)s[j][k] * (u32)sizeof(T));
+#pragma unroll
+    for (int j = 0; j < WS_R; j++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) ws_ldg_if(v[j][k], s[j][k], p.hub, p.x + s[j][k], s[j][k] < p.n_hot ? pol_keep : pol_stream);
+#endif
+}
+
+// what a warp carries from one stage to the next
+struct WsState {
+    double lane_acc;       // partial sum of the open row: spread over the lanes, or in lane 31 only
+    bool spread;
+    bool cont;             // the tile's first row started in an earlier tile (its sum goes to head[tile])
+    int row_base;          // row of the next row end
+    int first_row;
+    int tile;
+};
+
+// One stage of WS_STAGE links: this lane owns 8 consecutive links of the stream (the build stores a stage lane-major
+// so that the two int4 loads stay coalesced); e = their end-of-row flags (bit k), v = their products in storage order.
+// Registers and shuffles only: a load here would sit behind every gather already queued in the SM's L1TEX FIFO.
+template <typename T>
+__device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, const u32 e, const double (&v)[8], const int lane,
+                                           const u32 lt, const u32 le, const u64 pol_first) {
+    const u32 FULL = 0xffffffffu;
+    const u32 H = __ballot_sync(FULL, e != 0);
+    if (H == 0) {
+        // inside one long row: per-lane partial, no cross-lane traffic
+        const double a = __dadd_rn(__dadd_rn(v[0], v[1]), __dadd_rn(v[2], v[3]));
+        const double b = __dadd_rn(__dadd_rn(v[4], v[5]), __dadd_rn(v[6], v[7]));
+        s.lane_acc = __dadd_rn(s.lane_acc, __dadd_rn(a, b));
+        s.spread = true;
+        return;
+    }
+    // sum of the open row so far -> lane 0
+    double c;
+    if (s.spread) c = warp_sum(s.lane_acc);
+    else c = __shfl_sync(FULL, s.lane_acc, 31);
+    if (lane != 0) c = 0.0;
+    // row ends before this lane / in the whole stage (counts are 0..8: four ballots over the bits of the count)
+    const u32 cnt = __popc(e);
+    const u32 b0 = __ballot_sync(FULL, cnt & 1u), b1 = __ballot_sync(FULL, cnt & 2u), b2 = __ballot_sync(FULL, cnt & 4u),
+              b3 = __ballot_sync(FULL, cnt & 8u);
+    const int before = __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+    const int total = __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
+    // tail of this lane: the links after its last row end (all of them, plus the carry in lane 0, when it has none)
+    const int last = e ? 31 - __clz(e) : -1;
+    double tail = e ? 0.0 : c;
+#pragma unroll
+    for (int k = 0; k < 8; k++) tail = __dadd_rn(tail, k > last ? v[k] : 0.0);
+    // segmented inclusive scan of the lane tails; a segment starts at every lane that holds a row end
+    const u32 hm = H & le;
+    const int start = hm ? 31 - __clz(hm) : 0;
+    double x = tail;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const bool take = lane - d >= start;
+        if (__ballot_sync(FULL, take) == 0) break;       // no segment reaches that far back: done
+        const double t = __shfl_up_sync(FULL, x, d);
+        if (take) x = __dadd_rn(x, t);
+    }
+    const double pre = __shfl_up_sync(FULL, x, 1);      // sum of the lanes before this one back to the last row end
+    s.lane_acc = (lane == 31) ? x : 0.0;
+    s.spread = false;
+    // this lane's rows, in storage order; the first one also owns what came before the lane
+    double acc = (lane == 0) ? c : pre;
+    int row = s.row_base + before;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        acc = __dadd_rn(acc, v[k]);
+        if (e & (1u << k)) {
+            if (s.cont && row == s.first_row) p.head_partial[s.tile] = acc;
+            else st_policy(p.y + row, (T)acc, pol_first);
+            row++;
+            acc = 0.0;
+        }
+    }
+    s.row_base += total;
+}
+
+template <typename T, bool VALUED>
+__global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (p.ctl->done) return;
+    u32 smem0;
+    asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(smem0) : "l"(smem_raw));
+    const u32 hub_addr = smem0 + WS_HDR;
+    u64 hub_gen;                                   // generic address of the hub table, opaque to ptxas (see iterate.cu)
+    asm volatile("mov.u64 %0, %1;" : "=l"(hub_gen) : "l"(smem_raw + WS_HDR));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    if (threadIdx.x == 0) mbar_init(reinterpret_cast<u64*>(smem_raw), 1);
+    __syncthreads();
+    if (p.hub > 0 && threadIdx.x == 0) {      // hub table: the first `hub` entries of x, TMA bulk copies (UBLKCP)
+        const u32 bytes = (u32)p.hub * (u32)sizeof(T);
+        mbar_expect_tx(reinterpret_cast<u64*>(smem_raw), bytes);
+        for (u32 off = 0; off < bytes; off += 32768) {
+            const u32 len = bytes - off < 32768 ? bytes - off : 32768;
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hub_addr + off),
+                         "l"(reinterpret_cast<const unsigned char*>(p.x) + off), "r"(len), "r"(smem0)
+                         : "memory");
+        }
+    }
+    const u64 pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+
+    const int gw = blockIdx.x * WS_WARPS + warp, GW = gridDim.x * WS_WARPS;
+    const int my_tiles = p.ws_tiles > gw ? (p.ws_tiles - gw + GW - 1) / GW : 0;
+    const int total = my_tiles * WS_SPT;       // stages of this warp (always even: WS_SPT is)
+    // link offset of this lane's first int4 in stage k of this warp's sequence (stages past the end re-read the last)
+    auto pos_of = [&](int k) -> size_t {
+        k = k < total ? k : total - 1;
+        return ((size_t)(gw + (k / WS_SPT) * GW) * WS_TILE) + (size_t)((k & (WS_SPT - 1)) * WS_STAGE + lane * 4);
+    };
+
+    if (total > 0) {
+        const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
+        // two register stages, A and B, used alternately (the loop is unrolled by two so that no register that is the
+        // target of a load in flight is ever copied): while stage X is being summed, the gathers of stage Y are in
+        // flight and the indices of the stage after that are on their way into X's index registers.
+        int4 ivA[WS_R], ivB[WS_R];
+        T gA[WS_R][4], gB[WS_R][4], wA[WS_R][4], wB[WS_R][4];
+        size_t posA = pos_of(0), posB = pos_of(1);
+#pragma unroll
+        for (int j = 0; j < WS_R; j++) {
+            ivA[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + posA + j * WS_STEP), pol_stream);
+            ivB[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + posB + j * WS_STEP), pol_stream);
+        }
+        u32 meta_next = p.ws_tile[gw];
+        if (p.hub > 0) mbar_wait_a(smem0, 0);
+        ws_gather_stage<T>(p, ivA, hub_gen, hub_addr, pol_keep, pol_stream, gA);
+        if (VALUED) {
+#pragma unroll
+            for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + posA + j * WS_STEP, pol_stream, wA[j]);
+        }
+        WsState s;
+        s.lane_acc = 0.0; s.spread = false; s.cont = false; s.row_base = 0; s.first_row = 0; s.tile = 0;
+
+#ifdef RWR_PROFILE_CLOCKS
+        double clk_sink = 0.0;
+#define WCLK_LAND_IDX(FL, IVY) if (FL == 77u && IVY[0].x == -7 && IVY[1].w == -7) clk_sink += 1.0;
+#define WCLK_LAND_G(GX) if (GX[0][0] + GX[0][1] + GX[0][2] + GX[0][3] + GX[1][0] + GX[1][1] + GX[1][2] + GX[1][3] == (T)-7) clk_sink += 1.0;
+#else
+#define WCLK_LAND_IDX(FL, IVY)
+#define WCLK_LAND_G(GX)
+#endif
+        WCLK_DECL;
+#define WS_HALF(K, IVX, GX, WX, POSX, IVY, GY, WY, POSY)                                                               \
+    {                                                                                                                  \
+        const u32 fl = ((u32)IVX[0].x >> 31) | (((u32)IVX[0].y >> 31) << 1) | (((u32)IVX[0].z >> 31) << 2) |           \
+                       (((u32)IVX[0].w >> 31) << 3) | (((u32)IVX[1].x >> 31) << 4) | (((u32)IVX[1].y >> 31) << 5) |    \
+                       (((u32)IVX[1].z >> 31) << 6) | (((u32)IVX[1].w >> 31) << 7);                                    \
+        WCLK_LAND_IDX(fl, IVY)                                                                                         \
+        WCLK(0);                                                                                                       \
+        /* gathers of the next stage, then the indices of the one after it into the registers just freed */            \
+        ws_gather_stage<T>(p, IVY, hub_gen, hub_addr, pol_keep, pol_stream, GY);                                       \
+        if (VALUED) {                                                                                                  \
+            _Pragma("unroll") for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + POSY + j * WS_STEP, pol_stream, WY[j]); \
+        }                                                                                                              \
+        WCLK(1);                                                                                                       \
+        POSX = pos_of((K) + 2);                                                                                        \
+        _Pragma("unroll") for (int j = 0; j < WS_R; j++)                                                               \
+            IVX[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + POSX + j * WS_STEP), pol_stream);         \
+        WCLK(2);                                                                                                       \
+        WCLK_LAND_G(GX)                                                                                                \
+        WCLK(3);                                                                                                       \
+        const int st = (K) & (WS_SPT - 1);                                                                             \
+        if (st == 0) {                                                                                                 \
+            s.tile = gw + ((K) / WS_SPT) * GW;                                                                         \
+            s.first_row = (int)(meta_next & 0x7fffffffu);                                                              \
+            s.cont = (meta_next >> 31) != 0;                                                                           \
+            s.row_base = s.first_row;                                                                                  \
+            s.lane_acc = 0.0;                                                                                          \
+            s.spread = false;                                                                                          \
+            const int nt = s.tile + GW;                                                                                \
+            meta_next = p.ws_tile[nt < p.ws_tiles ? nt : p.ws_tiles];                                                  \
+        }                                                                                                              \
+        {                                                                                                              \
+            double v[8];                                                                                               \
+            _Pragma("unroll") for (int j = 0; j < WS_R; j++)                                                           \
+                _Pragma("unroll") for (int i = 0; i < 4; i++)                                                          \
+                    v[j * 4 + i] = VALUED ? (double)mul_rn(GX[j][i], WX[j][i]) : (double)GX[j][i];                     \
+            ws_consume<T>(p, s, fl, v, lane, lt, le, pol_stream);                                                      \
+        }                                                                                                              \
+        WCLK(4);                                                                                                       \
+        if (st == WS_SPT - 1) {                                                                                        \
+            const double c = s.spread ? warp_sum(s.lane_acc) : __shfl_sync(0xffffffffu, s.lane_acc, 31);               \
+            if (lane == 0) p.carry[s.tile] = c;                                                                        \
+        }                                                                                                              \
+        WCLK(5);                                                                                                       \
+    }
+
+        for (int k = 0; k < total; k += 2) {
+            WS_HALF(k, ivA, gA, wA, posA, ivB, gB, wB, posB)
+            WS_HALF(k + 1, ivB, gB, wB, posB, ivA, gA, wA, posA)
+        }
+#undef WS_HALF
+        WCLK_FLUSH;
+#ifdef RWR_PROFILE_CLOCKS
+        if (clk_sink == -1.0) p.carry[0] = clk_sink;
+#endif
+    }
+}
+
+// rows cut by a tile boundary: their pieces (tails of the earlier tiles, head of the tile they end in) are added in
+// tile order and stored like any other row sum
+template <typename T>
+__global__ void __launch_bounds__(FIX_THREADS) k_cutrows_ws(const IterParams<T> p) {
+    if (p.ctl->done) return;
+    const int t = blockIdx.x * FIX_THREADS + threadIdx.x;
+    if (t >= p.ws_tiles) return;
+    const u32 meta = p.ws_tile[t];
+    const int row = (int)(meta & 0x7fffffffu);
+    const int next_row = (int)(p.ws_tile[t + 1] & 0x7fffffffu);
+    if ((meta >> 31) && next_row > row) {                 // a row from an earlier tile ends inside this tile
+        int m = t - 1;
+        while (m > 0 && p.ws_tile[m] == meta) m--;         // tiles lying wholly inside the row: same row, continued
+        double total = 0.0;
+        for (int i = m; i < t; i++) total = __dadd_rn(total, p.carry[i]);
+        total = __dadd_rn(total, p.head_partial[t]);
+        p.y[row] = (T)total;
+    }
+}
+
+// The per-row epilogue of Model.cs:84-97 on the finished pull sums, streamed and coalesced:
+//   y_t (+ S for the seed row, + S/N everywhere for the uniform restart), next x_t = fl(fl((1-c) y_t) * inv_t),
+//   restart mass and L1 residual partials; the last block adds the partials in a fixed order -> next S, residual,
+//   iteration count, convergence flag (Model.cs:57-66, :110-115).
+template <typename T, bool RESID>
+__global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p, double thr, int use_thr) {
+    __shared__ double scratch[2 * FIN_THREADS / 32];
+    __shared__ int is_last;
+    IterCtl* ctl = p.ctl;
+    if (ctl->done) return;
+    const double S = ctl->S;
+    const T uni_add = (T)((p.seed < 0) ? S * p.inv_n : 0.0);
+    const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
+    double accS = 0.0, accR = 0.0;
+    for (int row = blockIdx.x * FIN_THREADS + threadIdx.x; row < p.n; row += gridDim.x * FIN_THREADS) {
+        T y = ld_stream(p.y + row, pol_first);
+        const T invr = ld_stream(p.inv + row, pol_first);
+        if (row == p.seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
+        if (p.seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
+        const T rw = mul_rn(p.omc, y);
+        // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
+        st_policy(p.x_next + row, mul_rn(rw, invr), row < p.n_hot ? pol_last : pol_first);
+        accS += (invr == (T)0) ? (double)y : (double)sub_rn(y, rw);
+        if (RESID) {
+            const T rp = ld_stream(p.r_prev + row, pol_first);
+            accR += (double)((rp > y) ? sub_rn(rp, y) : sub_rn(y, rp));
+        }
+    }
+    block_sum2<FIN_THREADS>(accS, accR, scratch);
+    if (threadIdx.x == 0) {
+        p.slot_S[blockIdx.x] = accS;
+        p.slot_R[blockIdx.x] = accR;
+        __threadfence();
+        const unsigned tk = atomicAdd(&ctl->ticket, 1u);
+        is_last = (tk == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double a = 0.0, b = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += FIN_THREADS) {
+            a += __ldcg(p.slot_S + i);
+            b += __ldcg(p.slot_R + i);
+        }
+        __syncthreads();
+        block_sum2<FIN_THREADS>(a, b, scratch);
+        if (threadIdx.x == 0) {
+            ctl->S = a;
+            ctl->resid = b;
+            ctl->iters += 1;
+            ctl->ticket = 0;
+            if (use_thr && b < thr) ctl->done = 1;        // strict `<` (Model.cs:114)
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ launch
+int ws_main_grid(const rwr_graph* g) {
+    return std::max(1, std::min(g->sm_count, (g->ws_tiles + WS_WARPS - 1) / WS_WARPS));
+}
+int ws_fix_grid(const rwr_graph* g) { return (int)div_up((size_t)std::max(g->ws_tiles, 1), FIX_THREADS); }
+int ws_fin_grid(const rwr_graph* g) {
+    return std::max(1, std::min(g->sm_count * 8, (int)div_up((size_t)std::max(g->n, 1), FIN_THREADS)));
+}
+
+template <typename T>
+void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
+    const bool valued = g->layout == RWR_LAYOUT_VALUED;
+    const size_t smem = (size_t)WS_HDR + (size_t)p.hub * sizeof(T);
+    auto kern = valued ? k_spmv_ws<T, true> : k_spmv_ws<T, false>;
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<ws_main_grid(g), WS_THREADS, smem, g->stream>>>(p);
+    KERNEL_CHECK();
+}
+template <typename T>
+void ws_launch_finish_only(rwr_graph* g, const IterParams<T>& p, bool resid, double thr, int use_thr) {
+    k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(p);
+    if (resid) k_finish_ws<T, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    else k_finish_ws<T, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    KERNEL_CHECK();
+}
+template <typename T>
+void ws_launch_iteration(rwr_graph* g, const IterParams<T>& p, bool resid, double thr, int use_thr) {
+    ws_launch_spmv_only<T>(g, p);
+    ws_launch_finish_only<T>(g, p, resid, thr, use_thr);
+    g->pool.launches += 3;
+}
+template void ws_launch_iteration<double>(rwr_graph*, const IterParams<double>&, bool, double, int);
+template void ws_launch_iteration<float>(rwr_graph*, const IterParams<float>&, bool, double, int);
+template void ws_launch_spmv_only<double>(rwr_graph*, const IterParams<double>&);
+template void ws_launch_spmv_only<float>(rwr_graph*, const IterParams<float>&);
+template void ws_launch_finish_only<double>(rwr_graph*, const IterParams<double>&, bool, double, int);
+template void ws_launch_finish_only<float>(rwr_graph*, const IterParams<float>&, bool, double, int);
+
+#ifdef RWR_PROFILE_CLOCKS
+extern "C" int rwr_debug_clocks_ws(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_clk_ws, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_clk_ws, z, sizeof(z)); }
+    return 0;
+}
+#endif
