@@ -133,11 +133,16 @@ void stream_prepare(rwr_graph* g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// Shared memory and L1 share the SM's 256 KB, and the L1 side is what holds the sectors of the gathers in flight: with
+// the maximum carve-out (228 KB shared) the kernel ran 2x slower than with none (profiles/microbench/hub_sweep.py).
+// Auto therefore stops at the 100 KB carve-out step in FP64 (~150 KB of L1 left) and at the 132 KB step in FP32,
+// the best points of the sweep on the C2 graph.
 int ws_hub_entries(const rwr_graph* g, int precision) {
     const size_t elt = precision == RWR_FP32 ? 4 : 8;
     if ((size_t)g->max_smem_optin <= (size_t)WS_HDR) return 0;
     long cap = (long)(((size_t)g->max_smem_optin - WS_HDR) / elt) & ~3L;
-    long want = g->opts.hub_entries < 0 ? cap : std::min<long>(cap, (long)g->opts.hub_entries & ~3L);
+    const long auto_cap = (long)(((precision == RWR_FP32 ? WS_HUB_AUTO_BYTES_FP32 : WS_HUB_AUTO_BYTES) - WS_HDR) / elt) & ~3L;
+    long want = g->opts.hub_entries < 0 ? std::min(cap, auto_cap) : std::min<long>(cap, (long)g->opts.hub_entries & ~3L);
     long n4 = ((long)g->n + 3) & ~3L;
     return (int)std::max<long>(0, std::min(want, n4));
 }
@@ -173,6 +178,17 @@ __device__ __forceinline__ void ws_gather_stage(const IterParams<T>& p, const in
 #pragma unroll
     for (int j = 0; j < WS_R; j++) {
         s[j][0] = iv[j].x & 0x7fffffff; s[j][1] = iv[j].y & 0x7fffffff; s[j][2] = iv[j].z & 0x7fffffff; s[j][3] = iv[j].w & 0x7fffffff;
+    }
+    if (p.debug >= 3) {                 // measurement only: 3 = no gathers, 4 = every gather from the hub, 5 = every gather from L2
+#pragma unroll
+        for (int j = 0; j < WS_R; j++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (p.debug == 3) { v[j][k] = (T)1; continue; }
+                if (p.debug == 4) s[j][k] = p.hub ? s[j][k] % p.hub : 0;
+                if (p.debug == 5) s[j][k] = p.hub + s[j][k] % (p.n - p.hub);
+            }
+        if (p.debug == 3) return;
     }
 #if WS_GATHER_GENERIC
     const u64 xg = (u64)(uintptr_t)p.x;
@@ -211,7 +227,7 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
                                            const u32 lt, const u32 le, const u64 pol_first) {
     const u32 FULL = 0xffffffffu;
     const u32 H = __ballot_sync(FULL, e != 0);
-    if (H == 0) {
+    if (H == 0 || p.debug == 1) {
         // inside one long row: per-lane partial, no cross-lane traffic
         const double a = __dadd_rn(__dadd_rn(v[0], v[1]), __dadd_rn(v[2], v[3]));
         const double b = __dadd_rn(__dadd_rn(v[4], v[5]), __dadd_rn(v[6], v[7]));
@@ -257,7 +273,7 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
         acc = __dadd_rn(acc, v[k]);
         if (e & (1u << k)) {
             if (s.cont && row == s.first_row) p.head_partial[s.tile] = acc;
-            else st_policy(p.y + row, (T)acc, pol_first);
+            else if (p.debug != 2) st_policy(p.y + row, (T)acc, pol_first);
             row++;
             acc = 0.0;
         }
