@@ -146,6 +146,9 @@ int rwr_run_fixed(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
  * bitwise fixed point exists); iters_out[n_seeds] receives the number of deliverRanks() calls.            */
 int rwr_run_threshold(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, double thr,
                       int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out);
+/* the same Model re-run from the constructor state with other seeds (same count): rank buffers are reused, no
+ * device allocation happens on the call.  The graph handle must still be alive.                             */
+int rwr_rerun_fixed(rwr_result* r, const int32_t* seeds, double c, int32_t n_iter);
 int rwr_result_get_info(rwr_result* r, rwr_run_info* info);
 /* `Model.rank` (Model.cs:7) of one seed, widened to double in FP32 mode                                    */
 int rwr_scores(rwr_result* r, int32_t seed_slot, double* out_n);

@@ -878,7 +878,8 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     const size_t ld = (n + 3) & ~(size_t)3;
     res->ld = ld;
-    Prec<T>::ybuf(res).alloc(std::max<size_t>(1, ld * (size_t)n_seeds), nullptr);
+    if (Prec<T>::ybuf(res).n != std::max<size_t>(1, ld * (size_t)n_seeds))      // a re-run keeps its rank buffers
+        Prec<T>::ybuf(res).alloc(std::max<size_t>(1, ld * (size_t)n_seeds), nullptr);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
     ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
@@ -1016,11 +1017,11 @@ template void iterate_single_into<double>(rwr_graph*, int, double, int, double*,
 template void iterate_single_into<float>(rwr_graph*, int, double, int, float*, float*, int64_t*);
 
 static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int mode, int32_t n_iter, double thr,
-                     int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out) {
+                     int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out, rwr_result* reuse = nullptr) {
     rwr_result* res = nullptr;
     try {
-        if (!out) RWR_FAIL(RWR_E_INVALID, "out is NULL");
-        *out = nullptr;
+        if (!out && !reuse) RWR_FAIL(RWR_E_INVALID, "out is NULL");
+        if (out) *out = nullptr;
         if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
         if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run (KeyNotFoundException at Model.cs:79)");
         if (g->comm) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned graphs run through rwr_run_fixed_partitioned");
@@ -1032,7 +1033,7 @@ static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double
             if (seeds[s] < -1 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);
         CUDA_CHECK(cudaSetDevice(g->device));
         if (mode == 1 && !(thr > 0.0)) thr = (1.0 / 1.7976931348623157e308) * (double)g->n;   // Model.cs:53
-        res = new rwr_result();
+        res = reuse ? reuse : new rwr_result();
         res->g = g;
         res->device = g->device;
         res->n_seeds = n_seeds;
@@ -1041,13 +1042,13 @@ static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double
         res->iters.assign(n_seeds, 0);
         if (precision == RWR_FP64) run_all<double>(g, res, seeds, n_seeds, c, mode, n_iter, thr, max_iter, iters_out);
         else run_all<float>(g, res, seeds, n_seeds, c, mode, n_iter, thr, max_iter, iters_out);
-        *out = res;
+        if (out) *out = res;
         return RWR_OK;
     } catch (const RwrError& e) {
-        delete res;
+        if (!reuse) delete res;
         return e.code;
     } catch (...) {
-        delete res;
+        if (!reuse) delete res;
         rwr_set_error("unexpected exception");
         return RWR_E_INVALID;
     }
@@ -1063,6 +1064,13 @@ int rwr_run_fixed(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
 int rwr_run_threshold(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, double thr, int32_t max_iter,
                       int32_t precision, int32_t* iters_out, rwr_result** out) {
     return run_entry(g, seeds, n_seeds, c, 1, 0, thr, max_iter, precision, iters_out, out);
+}
+
+// `new Model(graph, c, seed).run(n)` again on a live Model object: same graph, seed count and precision, the rank
+// buffers are reused (no device allocation on the call).
+int rwr_rerun_fixed(rwr_result* r, const int32_t* seeds, double c, int32_t n_iter) {
+    if (!r || !r->g) { rwr_set_error("NULL result"); return RWR_E_INVALID; }
+    return run_entry(r->g, seeds, r->n_seeds, c, 0, n_iter, 0.0, 0, r->precision, nullptr, nullptr, r);
 }
 
 int rwr_result_get_info(rwr_result* r, rwr_run_info* info) {

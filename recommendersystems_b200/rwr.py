@@ -230,6 +230,13 @@ class _Result:
         _check(N.lib().rwr_result_get_info(self._h, C.byref(i)))
         return i
 
+    def rerun(self, seeds: Sequence[int], c: float, n_iter: int) -> None:
+        """The same Model object run again from its constructor state with other seeds; no device allocation."""
+        s = np.ascontiguousarray(seeds, np.int32)
+        if len(s) != self.n_seeds:
+            raise ValueError("rerun() needs the same number of seeds")
+        _check(N.lib().rwr_rerun_fixed(self._h, _p(s), float(c), int(n_iter)))
+
     def scores(self, slot: int = 0) -> np.ndarray:
         out = np.empty(self.n_nodes, np.float64)
         _check(N.lib().rwr_scores(self._h, slot, _p(out)))

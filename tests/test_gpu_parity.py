@@ -438,3 +438,68 @@ def test_batched_spmm_matches_oracle_and_single_column(unit):
         assert np.abs(sc32[i, :cnt32[i]] - osc).max() <= 2e-6 * max(osc.max(), 1e-30) + 1e-30
     with pytest.raises(KeyError):
         rec.RecommendationBatch([seeds[0], int(np.flatnonzero(raw_deg == 0)[0])], 0.15, 3, 5)
+
+
+# ------------------------------------------------------------------------------------------ Model re-run (buffers reused)
+@pytest.mark.parametrize("prec", [rs.FP64, rs.FP32])
+def test_rerun_reuses_the_model_and_matches_a_fresh_run(prec):
+    g = load_golden("small_b")
+    gg = gpu_graph(g["input"])
+    deg = gg.degrees(raw=True)
+    users = [int(u) for u in np.flatnonzero(deg > 0)[:4]]
+    m = run_fixed(gg, [users[0]], C015, 7, prec)
+    for seed, n_iter in ((users[1], 7), (users[2], 3), (users[0], 11)):
+        m.rerun([seed], C015, n_iter)
+        fresh = run_fixed(gg, [seed], C015, n_iter, prec)
+        assert np.array_equal(m.scores(0), fresh.scores(0))          # same kernels, same order: bit-identical
+        assert m.info().iterations == n_iter
+        fresh.close()
+    with pytest.raises(ValueError):
+        m.rerun(users[:2], C015, 3)
+    with pytest.raises(KeyError):
+        m.rerun([gg.size()], C015, 3)
+    m.close()
+
+
+def test_rows_without_in_links_and_tile_cuts():
+    """Edge-stream corner cases: rows with no in-links (padding link to the zero entry), a hub row spanning several
+    8192-link tiles, rows ending exactly on a tile boundary; seeds inside each kind of row."""
+    rng = np.random.default_rng(5)
+    n = 30_000
+    hub = 7
+    src, dst = [], []
+    # hub row of W^T: ~40k in-links (5 tiles); sources are distinct nodes each with a single out-link or two
+    s = rng.choice(np.arange(100, n), size=20_000, replace=False)
+    src += s.tolist(); dst += [hub] * len(s)
+    # a band of nodes 8..60 that only have out-links (no in-links), pointing at random targets
+    for u in range(8, 60):
+        t = rng.choice(np.arange(1000, 2000), size=5, replace=False)
+        src += [u] * 5; dst += t.tolist()
+    # random background
+    a = rng.integers(60, n, size=60_000); b = rng.integers(60, n, size=60_000)
+    keep = a != b
+    src += a[keep].tolist(); dst += b[keep].tolist()
+    order = np.argsort(np.asarray(src), kind="stable")
+    src = np.asarray(src, np.int32)[order]; dst = np.asarray(dst, np.int32)[order]
+    key = src.astype(np.int64) * n + dst
+    _, first = np.unique(key, return_index=True)
+    first.sort()
+    src, dst = src[first], dst[first]
+    inp = dict(node_id=np.arange(n, dtype=np.int64) + 10_000, node_type=np.where(np.arange(n) % 3 == 0, 1, 2).astype(np.int32),
+               src=src, dst=dst, etype=np.full(len(src), 2, np.int32), w=np.ones(len(src)))
+    og = oracle_graph(inp)
+    for opts in (dict(), dict(relabel=False), dict(layout=N.LAYOUT_VALUED), dict(hub_entries=0)):
+        gg = gpu_graph(inp, **opts)
+        for seed in (hub, 10, int(src[-1]), int(s[0])):
+            want, _ = og.run(seed, C015, n_iter=6)
+            r = run_fixed(gg, [seed], C015, 6)
+            assert_close_fp64(r.scores(0), want, f"seed {seed} {opts}")
+            r.close()
+            r32 = run_fixed(gg, [seed], C015, 6, rs.FP32)
+            assert_close_fp32(r32.scores(0), want, f"fp32 seed {seed} {opts}")
+            r32.close()
+        res, it = run_threshold(gg, [hub], C015, 1e-9 * n, max_iter=200)
+        _, want_it = og.run(hub, C015, threshold=1e-9 * n)
+        assert int(it[0]) == want_it
+        res.close()
+        gg.close()
