@@ -1,0 +1,89 @@
+// RwrNative.cs -- P/Invoke bindings of librwr_b200.so (include/rwr_b200.h), one [DllImport] per exported symbol.
+// Shipped as source for the maintainers of Recommenders.dll; not compiled in this repository (no C# toolchain here).
+// Replaces nothing by itself: Graph.cs / Model.cs / Recommender.cs in this directory forward to it.
+using System;
+using System.Collections.Generic;
+using System.Runtime.InteropServices;
+
+namespace Recommenders.RWRBased.Native {
+    public enum RwrStatus {
+        OK = 0, E_INVALID = -1, E_BADSEED = -2, E_ALREADY_BUILT = -3, E_BADINDEX = -4, E_NOT_BUILT = -5,
+        E_CUDA = -6, E_NCCL = -7, E_OOM = -8, E_UNSUPPORTED = -9
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct RwrOpts {
+        public int device, layout, relabel, hub_entries, batch_width, kernel;
+        public ulong stream;
+        public int hot_min_degree, reserved1;
+        public static RwrOpts Default() { return new RwrOpts { device = -1, hub_entries = -1 }; }
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct RwrRunInfo {
+        public int n_seeds, n_nodes, precision, iterations;
+        public double residual;
+        public float iterate_ms, total_ms;
+        public long kernel_launches;
+    }
+
+    public sealed class GraphHandle : SafeHandle {
+        public GraphHandle() : base(IntPtr.Zero, true) { }
+        public override bool IsInvalid { get { return handle == IntPtr.Zero; } }
+        protected override bool ReleaseHandle() { RwrNative.rwr_graph_destroy(handle); return true; }
+    }
+    public sealed class ResultHandle : SafeHandle {
+        public ResultHandle() : base(IntPtr.Zero, true) { }
+        public override bool IsInvalid { get { return handle == IntPtr.Zero; } }
+        protected override bool ReleaseHandle() { RwrNative.rwr_result_destroy(handle); return true; }
+    }
+
+    public static class RwrNative {
+        const string Lib = "rwr_b200";          // librwr_b200.so on Linux (mono / .NET probe the lib prefix)
+        public const int FP64 = 0, FP32 = 1;
+
+        [DllImport(Lib)] public static extern int rwr_abi_version();
+        [DllImport(Lib)] public static extern int rwr_device_count();
+        [DllImport(Lib)] static extern IntPtr rwr_last_error();
+
+        [DllImport(Lib)] public static extern int rwr_graph_create(int nNodes, long[] nodeId, int[] nodeType, long nLinks,
+            int[] src, int[] dst, int[] etype, double[] w, ref RwrOpts opts, out GraphHandle graph);
+        [DllImport(Lib)] public static extern int rwr_graph_build(GraphHandle g);
+        [DllImport(Lib)] public static extern int rwr_graph_get_csr(GraphHandle g, long[] rowPtr, int[] col, double[] val);
+        [DllImport(Lib)] public static extern int rwr_graph_get_degrees(GraphHandle g, int[] outDegree, int[] rawDegree);
+        [DllImport(Lib)] public static extern void rwr_graph_destroy(IntPtr g);
+
+        [DllImport(Lib)] public static extern int rwr_run_fixed(GraphHandle g, int[] seeds, int nSeeds, double c, int nIter,
+            int precision, out ResultHandle result);
+        [DllImport(Lib)] public static extern int rwr_run_threshold(GraphHandle g, int[] seeds, int nSeeds, double c, double thr,
+            int maxIter, int precision, int[] itersOut, out ResultHandle result);
+        [DllImport(Lib)] public static extern int rwr_rerun_fixed(ResultHandle r, int[] seeds, double c, int nIter);
+        [DllImport(Lib)] public static extern int rwr_result_get_info(ResultHandle r, out RwrRunInfo info);
+        [DllImport(Lib)] public static extern int rwr_scores(ResultHandle r, int seedSlot, double[] outN);
+        [DllImport(Lib)] public static extern int rwr_topk(ResultHandle r, int k, long[] outIds, double[] outScores, int[] outCounts);
+        [DllImport(Lib)] public static extern int rwr_rank_all(ResultHandle r, int seedSlot, long[] ids, double[] scores, long cap,
+            out long count);
+        [DllImport(Lib)] public static extern void rwr_result_destroy(IntPtr r);
+
+        [DllImport(Lib)] public static extern int rwr_recommend(GraphHandle g, int[] seeds, int nSeeds, double c, int nIter,
+            int precision, int k, long[] outIds, double[] outScores, int[] outCounts, out RwrRunInfo info);
+        [DllImport(Lib)] public static extern int rwr_evaluate(long[] rankedIds, long n, long[] testIds, long nTest, out int hits,
+            out double avgPrecision);
+
+        public static string LastError() { return Marshal.PtrToStringAnsi(rwr_last_error()) ?? ""; }
+
+        // Status codes -> the exception types the managed implementation throws at the cited lines.
+        public static void Check(int rc) {
+            if (rc == 0) return;
+            string msg = LastError();
+            switch ((RwrStatus)rc) {
+                case RwrStatus.E_BADSEED:                                      // Recommender.cs:21
+                case RwrStatus.E_NOT_BUILT: throw new KeyNotFoundException(msg);   // Model.cs:79
+                case RwrStatus.E_ALREADY_BUILT: throw new ArgumentException(msg);  // Graph.cs:86 (Dictionary.Add)
+                case RwrStatus.E_BADINDEX: throw new IndexOutOfRangeException(msg); // Model.cs:87
+                case RwrStatus.E_OOM: throw new OutOfMemoryException(msg);
+                default: throw new InvalidOperationException("librwr_b200 error " + rc + ": " + msg);
+            }
+        }
+    }
+}

@@ -135,7 +135,7 @@ void stream_prepare(rwr_graph* g) {
 
 // Shared memory and L1 share the SM's 256 KB, and the L1 side is what holds the sectors of the gathers in flight: with
 // the maximum carve-out (228 KB shared) the kernel ran 2x slower than with none (profiles/microbench/hub_sweep.py).
-// Auto therefore stops at the 100 KB carve-out step in FP64 (~150 KB of L1 left) and at the 132 KB step in FP32,
+// Auto therefore stops at the 100 KB carve-out step in FP64 (~156 KB of L1 left) and at the 164 KB step in FP32,
 // the best points of the sweep on the C2 graph.
 int ws_hub_entries(const rwr_graph* g, int precision) {
     const size_t elt = precision == RWR_FP32 ? 4 : 8;

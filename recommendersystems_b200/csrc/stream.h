@@ -12,8 +12,8 @@ constexpr int WS_TILE = 8192;                    // links per tile (unit of work
 constexpr int WS_SPT = WS_TILE / WS_STAGE;       // 32 stages per tile
 constexpr int WS_HDR = 128;                      // mbarrier, ahead of the hub table
 constexpr int FIN_THREADS = 256;
-constexpr size_t WS_HUB_AUTO_BYTES = 100 * 1024;        // shared-memory carve-out step the automatic hub size stays within (FP64)
-constexpr size_t WS_HUB_AUTO_BYTES_FP32 = 132 * 1024;   // same, FP32
+constexpr size_t WS_HUB_AUTO_BYTES = 99 * 1024;         // automatic hub size, FP64: fits the 100 KB carve-out step with the 1 KB the system reserves
+constexpr size_t WS_HUB_AUTO_BYTES_FP32 = 163 * 1024;   // same, FP32: the 164 KB step
 static_assert(WS_R == 2, "ws_consume is written for two rounds (8 links per lane) per stage");
 
 template <typename T> struct IterParams;
