@@ -97,6 +97,9 @@ typedef struct rwr_graph_info {
     float build_ms;          /* rwr_graph_build device time (CUDA events)                                       */
     float synth_ms;          /* rwr_synth_create device time                                                    */
     int64_t device_bytes;    /* device memory held by the handle                                                */
+    int32_t row_begin, row_end;  /* rows of W^T (internal labels) this rank iterates on: [0, N) unless partitioned   */
+    int32_t n_ranks;         /* 1 unless the graph was created with rwr_*_create_partitioned                    */
+    int32_t reserved;
 } rwr_graph_info;
 
 typedef struct rwr_run_info {
@@ -176,12 +179,18 @@ int rwr_profile_iteration(rwr_graph* g, int32_t seed, double c, int32_t precisio
 int rwr_evaluate(const int64_t* ranked_ids, int64_t n, const int64_t* test_ids, int64_t n_test, int32_t* hits,
                  double* avg_precision);
 
-/* ---- row-partitioned single graph (no reference analogue): slices of W^T + NCCL allGather per iteration ---- */
+/* ---- row-partitioned single graph (no reference analogue): slices of W^T + NCCL allGather per iteration ----
+ * One process per GPU.  Rank 0 calls rwr_comm_unique_id and hands the 128 bytes to the other ranks by any means
+ * (the tests use torch.distributed); every rank then calls rwr_comm_create (opts->device picks the GPU) and one of
+ * the *_create_partitioned functions with the SAME input, then rwr_graph_build.  From there rwr_run_fixed /
+ * rwr_run_threshold / rwr_scores / rwr_topk / rwr_rank_all / rwr_recommend (k <= 16) are collective calls: every
+ * rank makes them with the same arguments and every rank receives the full result.  The communicator must outlive
+ * the graphs created on it.  NCCL (libnccl.so.2) is bound at run time; RWR_NCCL_LIB overrides the path.          */
 typedef struct rwr_comm rwr_comm;
 int rwr_comm_unique_id(void* id128 /* 128 bytes */);
 int rwr_comm_create(int32_t rank, int32_t n_ranks, const void* id128, const rwr_opts* opts, rwr_comm** out);
 void rwr_comm_destroy(rwr_comm* c);
-/* every rank generates the same graph and keeps the rows of W^T it owns (balanced by nnz)                  */
+/* every rank generates the same graph and keeps the rows of W^T it owns (balanced by link count)           */
 int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_comm* comm, rwr_graph** out);
 int rwr_graph_create_partitioned(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
                                  const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,

@@ -5,9 +5,9 @@ NodeType, EdgeType) on top of the C ABI of librwr_b200.so (include/rwr_b200.h). 
 extension must be built (`python -c "import __graft_entry__ as g; g.build()"`) and a CUDA device must be present
 for anything that computes.
 """
-from .rwr import (EdgeType, ForwardLink, Graph, Model, Node, NodeType, Recommender, RwrError, SynthSpec,
+from .rwr import (Comm, EdgeType, ForwardLink, Graph, Model, Node, NodeType, Recommender, RwrError, SynthSpec,
                   FP32, FP64, evaluate, widen_float)
 from . import _native
 
-__all__ = ["EdgeType", "ForwardLink", "Graph", "Model", "Node", "NodeType", "Recommender", "RwrError", "SynthSpec",
+__all__ = ["Comm", "EdgeType", "ForwardLink", "Graph", "Model", "Node", "NodeType", "Recommender", "RwrError", "SynthSpec",
            "FP32", "FP64", "evaluate", "widen_float", "_native"]

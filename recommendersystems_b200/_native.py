@@ -35,7 +35,8 @@ class rwr_graph_info(C.Structure):
                 ("n_dangling", C.c_int32), ("layout", C.c_int32), ("relabelled", C.c_int32), ("n_hot", C.c_int32),
                 ("hub_entries_fp64", C.c_int32), ("hub_entries_fp32", C.c_int32), ("n_chunks", C.c_int32),
                 ("max_in_degree", C.c_int32), ("max_out_degree", C.c_int32), ("build_ms", C.c_float),
-                ("synth_ms", C.c_float), ("device_bytes", C.c_int64)]
+                ("synth_ms", C.c_float), ("device_bytes", C.c_int64), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("n_ranks", C.c_int32), ("reserved", C.c_int32)]
 
 
 class rwr_run_info(C.Structure):

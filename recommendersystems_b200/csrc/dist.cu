@@ -1,33 +1,199 @@
-// dist.cu -- row-partitioned mode (K10): placeholder entry points until the NCCL path lands.
-#include "graph.h"
+// dist.cu -- K10: row-partitioned mode for one graph spread over several GPUs (no reference analogue).
+//
+// Every rank owns a contiguous block of rows of W^T (the destination nodes), balanced by link count, with its own
+// edge stream (stream.cu).  An iteration on a rank needs the whole gather vector x and produces the slice of the next
+// one for its rows, so after every iteration the slices are allGathered over NVLink / NVSwitch (one grouped set of
+// in-place ncclBroadcast calls: slices have unequal lengths) and the two scalars every rank needs -- the restart mass S
+// and the L1 residual -- are summed with a 16-byte ncclAllReduce.  NCCL is bound at run time (dlopen) so that a
+// single-GPU host needs no NCCL at all.
+#include <dlfcn.h>
+
+#include <mutex>
+
+#include "dist.h"
+
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclInt8 = 0, ncclChar = 0, ncclFloat64 = 8 };      // nccl.h (2.x): ncclDataType_t
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    int (*CommDestroy)(ncclComm_t) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+std::string g_nccl_err;
+
+void load_nccl() {
+    const char* names[] = {getenv("RWR_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { g_nccl_err = "libnccl.so.2 not found (set RWR_NCCL_LIB)"; return; }
+#define BIND(field, sym)                                                        \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.lib, sym);                          \
+    if (!g_nccl.field) { g_nccl_err = std::string("NCCL symbol missing: ") + sym; g_nccl.lib = nullptr; return; }
+    BIND(GetUniqueId, "ncclGetUniqueId")
+    BIND(CommInitRank, "ncclCommInitRank")
+    BIND(CommDestroy, "ncclCommDestroy")
+    BIND(Broadcast, "ncclBroadcast")
+    BIND(AllReduce, "ncclAllReduce")
+    BIND(GroupStart, "ncclGroupStart")
+    BIND(GroupEnd, "ncclGroupEnd")
+    BIND(GetErrorString, "ncclGetErrorString")
+#undef BIND
+}
+
+NcclApi& nccl() {
+    std::call_once(g_nccl_once, load_nccl);
+    if (!g_nccl.lib) RWR_FAIL(RWR_E_NCCL, "%s", g_nccl_err.c_str());
+    return g_nccl;
+}
+
+#define NCCL_CHECK(expr)                                                                              \
+    do {                                                                                              \
+        int rc__ = (expr);                                                                            \
+        if (rc__ != ncclSuccess) RWR_FAIL(RWR_E_NCCL, "%s failed: %s", #expr, nccl().GetErrorString(rc__)); \
+    } while (0)
+
+}  // namespace
 
 struct rwr_comm {
-    int rank = 0, n_ranks = 1;
+    int rank = 0, n_ranks = 1, device = 0;
+    ncclComm_t comm = nullptr;
 };
+
+int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
+int dist_n_ranks(const rwr_comm* c) { return c ? c->n_ranks : 1; }
+
+__global__ void k_dist_noop() {}
+
+void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
+    rwr_comm* c = g->comm;
+    if (!c || c->n_ranks < 2) return;
+    NcclApi& api = nccl();
+    NCCL_CHECK(api.GroupStart());
+    for (int r = 0; r < c->n_ranks; r++) {
+        const size_t b = (size_t)g->part_rows[r], e = (size_t)g->part_rows[r + 1];
+        if (e == b) continue;
+        unsigned char* ptr = (unsigned char*)vec + b * elt;
+        NCCL_CHECK(api.Broadcast(ptr, ptr, (e - b) * elt, ncclInt8, r, c->comm, g->stream));
+    }
+    NCCL_CHECK(api.GroupEnd());
+}
+
+void dist_exchange(rwr_graph* g, void* x_next, size_t elt, double* two_doubles) {
+    rwr_comm* c = g->comm;
+    if (!c || c->n_ranks < 2) return;
+    dist_allgather_rows(g, x_next, elt);
+    NCCL_CHECK(nccl().AllReduce(two_doubles, two_doubles, 2, ncclFloat64, ncclSum, c->comm, g->stream));
+}
+
+void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // synth.cu
 
 extern "C" {
 
 int rwr_comm_unique_id(void* id128) {
-    (void)id128;
-    rwr_set_error("row-partitioned mode is not built yet");
-    return RWR_E_UNSUPPORTED;
+    RWR_API_BEGIN
+    if (!id128) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    ncclUniqueId id;
+    NCCL_CHECK(nccl().GetUniqueId(&id));
+    memcpy(id128, &id, sizeof(id));
+    return RWR_OK;
+    RWR_API_END
 }
-int rwr_comm_create(int32_t, int32_t, const void*, const rwr_opts*, rwr_comm** out) {
-    if (out) *out = nullptr;
-    rwr_set_error("row-partitioned mode is not built yet");
-    return RWR_E_UNSUPPORTED;
+
+int rwr_comm_create(int32_t rank, int32_t n_ranks, const void* id128, const rwr_opts* opts, rwr_comm** out) {
+    rwr_comm* c = nullptr;
+    try {
+        if (!out || !id128) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+        *out = nullptr;
+        if (n_ranks < 1 || rank < 0 || rank >= n_ranks) RWR_FAIL(RWR_E_INVALID, "rank %d of %d", rank, n_ranks);
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) RWR_FAIL(RWR_E_CUDA, "no CUDA device");
+        c = new rwr_comm();
+        c->rank = rank;
+        c->n_ranks = n_ranks;
+        if (opts && opts->device >= 0) CUDA_CHECK(cudaSetDevice(opts->device));
+        CUDA_CHECK(cudaGetDevice(&c->device));
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NCCL_CHECK(nccl().CommInitRank(&c->comm, n_ranks, id, rank));
+        *out = c;
+        return RWR_OK;
+    } catch (const RwrError& e) {
+        delete c;
+        return e.code;
+    } catch (...) {
+        delete c;
+        rwr_set_error("unexpected exception");
+        return RWR_E_INVALID;
+    }
 }
-void rwr_comm_destroy(rwr_comm* c) { delete c; }
-int rwr_synth_create_partitioned(const rwr_synth_spec*, const rwr_opts*, rwr_comm*, rwr_graph** out) {
-    if (out) *out = nullptr;
-    rwr_set_error("row-partitioned mode is not built yet");
-    return RWR_E_UNSUPPORTED;
+
+void rwr_comm_destroy(rwr_comm* c) {
+    if (!c) return;
+    if (c->comm && g_nccl.lib) {
+        cudaSetDevice(c->device);
+        g_nccl.CommDestroy(c->comm);
+    }
+    delete c;
 }
-int rwr_graph_create_partitioned(int32_t, const int64_t*, const int32_t*, int64_t, const int32_t*, const int32_t*,
-                                 const int32_t*, const double*, const rwr_opts*, rwr_comm*, rwr_graph** out) {
-    if (out) *out = nullptr;
-    rwr_set_error("row-partitioned mode is not built yet");
-    return RWR_E_UNSUPPORTED;
+
+int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links, const int32_t* src,
+                          const int32_t* dst, const int32_t* etype, const double* w, const rwr_opts* opts, rwr_comm* comm,
+                          rwr_graph** out);                               // graph.cu
+
+// Every rank generates the same graph (the generator is deterministic); rwr_graph_build then keeps this rank's rows.
+int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_comm* comm, rwr_graph** out) {
+    rwr_graph* g = nullptr;
+    try {
+        if (!out || !spec || !comm) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+        *out = nullptr;
+        g = new rwr_graph();
+        rwr_opts o;
+        if (opts) o = *opts; else { memset(&o, 0, sizeof(o)); o.hub_entries = -1; }
+        o.device = comm->device;
+        if (o.kernel != 0) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned graphs run the warp-streamed kernel (rwr_opts.kernel = 0) only");
+        graph_init_device(g, &o);
+        g->comm = comm;
+        synth_generate_device(g, spec);
+        *out = g;
+        return RWR_OK;
+    } catch (const RwrError& e) {
+        rwr_graph_destroy(g);
+        return e.code;
+    } catch (...) {
+        rwr_graph_destroy(g);
+        rwr_set_error("unexpected exception");
+        return RWR_E_INVALID;
+    }
+}
+
+// Every rank passes the same link list.
+int rwr_graph_create_partitioned(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                                 const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                                 const rwr_opts* opts, rwr_comm* comm, rwr_graph** out) {
+    if (!comm) { rwr_set_error("NULL communicator"); return RWR_E_INVALID; }
+    rwr_opts o;
+    if (opts) o = *opts; else { memset(&o, 0, sizeof(o)); o.hub_entries = -1; }
+    o.device = comm->device;
+    if (o.kernel != 0) { rwr_set_error("row-partitioned graphs run the warp-streamed kernel (rwr_opts.kernel = 0) only"); return RWR_E_UNSUPPORTED; }
+    return rwr_graph_create_flat(n_nodes, node_id, node_type, n_links, src, dst, etype, w, &o, comm, out);
 }
 
 }  // extern "C"

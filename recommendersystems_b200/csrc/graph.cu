@@ -526,9 +526,20 @@ static void graph_build_impl(rwr_graph* g) {
 // ------------------------------------------------------------------------------------------------ C ABI
 extern "C" {
 
+int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                          const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                          const rwr_opts* opts, rwr_comm* comm, rwr_graph** out);
+
 int rwr_graph_create(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
                      const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
                      const rwr_opts* opts, rwr_graph** out) {
+    return rwr_graph_create_flat(n_nodes, node_id, node_type, n_links, src, dst, etype, w, opts, nullptr, out);
+}
+
+// shared by rwr_graph_create and rwr_graph_create_partitioned (dist.cu): `comm` marks a row-partitioned graph
+int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t* node_type, int64_t n_links,
+                          const int32_t* src, const int32_t* dst, const int32_t* etype, const double* w,
+                          const rwr_opts* opts, rwr_comm* comm, rwr_graph** out) {
     rwr_graph* g = nullptr;
     RWR_API_BEGIN
     if (!out) RWR_FAIL(RWR_E_INVALID, "out is NULL");
@@ -540,6 +551,7 @@ int rwr_graph_create(int32_t n_nodes, const int64_t* node_id, const int32_t* nod
     if ((u64)n_links >= (1ULL << 32) - 65536) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 links per device");
     g = new rwr_graph();
     graph_init_device(g, opts);
+    g->comm = comm;
     cudaStream_t st = g->stream;
     g->n = n_nodes;
     g->e0 = n_links;
@@ -605,6 +617,9 @@ int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info) {
     info->hub_entries_fp64 = g->built ? hub_entries_for(g, RWR_FP64) : 0;
     info->hub_entries_fp32 = g->built ? hub_entries_for(g, RWR_FP32) : 0;
     info->n_chunks = g->n_chunks;
+    info->row_begin = g->row_begin;
+    info->row_end = g->built ? g->row_end : 0;
+    info->n_ranks = g->part_rows.empty() ? 1 : (int32_t)g->part_rows.size() - 1;
     info->max_in_degree = (int32_t)g->max_in_degree;
     info->max_out_degree = (int32_t)g->max_out_degree;
     info->build_ms = g->build_ms;

@@ -77,6 +77,7 @@ struct rwr_graph {
     // ---- row-partitioned mode
     rwr_comm* comm = nullptr;
     int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
+    std::vector<int> part_rows;           // [n_ranks + 1] first row of every rank's slice
 
     float build_ms = 0.f, synth_ms = 0.f;
     int sm_count = 148;

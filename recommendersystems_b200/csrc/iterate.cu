@@ -23,6 +23,7 @@
 
 #include "iterate_dev.cuh"
 #include "stream.h"
+#include "dist.h"
 
 
 // ------------------------------------------------------------------------------------------------ K7 (variant): pipelined SpMV, rwr_opts.kernel = 1
@@ -681,6 +682,11 @@ __global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ 
     if (i < n) out[i] = (float)in[i];
 }
 
+// threshold mode on a row slice: the test of Model.cs:114 on the residual summed over all ranks
+__global__ void k_converged(IterCtl* ctl, double thr) {
+    if (!ctl->done && ctl->resid < thr) ctl->done = 1;
+}
+
 template <typename T>
 __global__ void k_unpermute(const T* __restrict__ y_int, const int32_t* __restrict__ new_of_old, int n, double* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -721,7 +727,7 @@ void ensure_fp32_arrays(rwr_graph* g) {
         if (g->n) k_f64_to_f32<<<div_up(g->n, 256), 256, 0, st>>>(g->inv64.p, g->inv32.p, g->n);
         KERNEL_CHECK();
     }
-    if (g->layout == RWR_LAYOUT_VALUED && !g->in_val32.p) {
+    if (g->layout == RWR_LAYOUT_VALUED && !g->in_val32.p && g->in_val64.p) {     // (a row slice keeps no whole-graph pull arrays)
         g->in_val32.alloc((size_t)g->nnz + IDX_PAD, &g->pool);
         if (g->nnz) k_f64_to_f32<<<div_up((size_t)g->nnz, 256), 256, 0, st>>>(g->in_val64.p, g->in_val32.p, (size_t)g->nnz);
         KERNEL_CHECK();
@@ -763,7 +769,19 @@ template <typename T>
 static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool write_y, bool resid, int main_grid, int fix_grid,
                              size_t smem, double thr, int use_thr) {
     cudaStream_t st = g->stream;
-    if (g->opts.kernel == 0) { ws_launch_iteration<T>(g, p, resid, thr, use_thr); return; }
+    if (g->opts.kernel == 0) {
+        const bool parted = dist_n_ranks(g->comm) > 1;
+        // on a row slice the convergence test needs the residual of all slices: it runs after the exchange
+        ws_launch_iteration<T>(g, p, resid, thr, parted ? 0 : use_thr);
+        if (parted) {
+            dist_exchange(g, p.x_next, sizeof(T), &p.ctl->S);        // IterCtl starts with { S, resid }
+            if (use_thr) {
+                k_converged<<<1, 1, 0, st>>>(p.ctl, thr);
+                KERNEL_CHECK();
+            }
+        }
+        return;
+    }
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
 #define LAUNCH(V, W, R)                                                                  \
     do {                                                                                 \
@@ -812,6 +830,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
     p.n_chunks = g->n_chunks; p.n = n; p.inv = Prec<T>::inv(g);
     p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
+    p.row_begin = g->row_begin; p.row_end = g->row_end;
     p.omc = (T)(1.0 - c);                                      // Model.cs:84 `(1 - dampingFactor)`
     p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot; p.debug = 0;
     p.head_partial = ws.head.p; p.carry = ws.carry.p;
@@ -863,6 +882,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
         // the rank of iteration h.iters sits in ya when h.iters is even (r0 was in ya), else in y_out
         if ((h.iters & 1) == 0 && n) CUDA_CHECK(cudaMemcpyAsync(y_out, ya, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     }
+    if (launched > 0) dist_allgather_rows(g, y_out, sizeof(T));       // row-partitioned: every rank gets the whole rank vector
     CUDA_CHECK(cudaEventRecord(ev1, st));
     CUDA_CHECK(cudaEventSynchronize(ev1));
     float ms = 0.f;
@@ -949,6 +969,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
     p.n_chunks = g->n_chunks; p.n = g->n; p.inv = Prec<T>::inv(g);
     p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
+    p.row_begin = g->row_begin; p.row_end = g->row_end;
     p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot;
     p.head_partial = ws.head.p; p.carry = ws.carry.p; p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
     p.r_prev = nullptr; p.y = ya;
@@ -1024,7 +1045,6 @@ static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double
         if (out) *out = nullptr;
         if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
         if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run (KeyNotFoundException at Model.cs:79)");
-        if (g->comm) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned graphs run through rwr_run_fixed_partitioned");
         if (n_seeds < 0 || (n_seeds && !seeds)) RWR_FAIL(RWR_E_INVALID, "bad seed list");
         if (mode == 0 && n_iter < 0) n_iter = 0;                     // `for (n = 0; n < nIterations; ..)` runs zero times
         if (precision != RWR_FP64 && precision != RWR_FP32) RWR_FAIL(RWR_E_INVALID, "unknown precision %d", precision);

@@ -23,6 +23,7 @@ struct IterParams {
     const T* ws_val;        // valued layout only
     const u32* ws_tile;     // [ws_tiles + 1] first row of a tile | continued-row flag in bit 31
     int ws_tiles;
+    int row_begin, row_end; // rows of W^T this rank owns ([0, n) unless the graph is row-partitioned)
     const T* x;             // gather source, internal labels
     const T* inv;
     const T* r_prev;        // previous rank (residual)

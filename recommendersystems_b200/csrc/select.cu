@@ -494,7 +494,8 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
         if (seeds[s] < -1 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);
         if (seeds[s] < 0) all_regular = false;
     }
-    if (k <= TOPK_MAX && all_regular && (n_seeds < 2 || g->opts.batch_width == 1)) {
+    // a row slice of a partitioned graph has no whole-graph pull CSR: seeds run one at a time through the edge stream
+    if (k <= TOPK_MAX && all_regular && (n_seeds < 2 || g->opts.batch_width == 1 || g->comm)) {
         if (precision == RWR_FP64) recommend_singles<double>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
         else recommend_singles<float>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
         return RWR_OK;

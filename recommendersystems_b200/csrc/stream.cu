@@ -27,6 +27,7 @@
 #include "iterate_dev.cuh"
 #include "primitives.cuh"
 #include "stream.h"
+#include "dist.h"
 
 constexpr u32 END_BIT = 0x80000000u;
 
@@ -50,6 +51,9 @@ __global__ void k_ws_len(const u32* __restrict__ in_ptr, int n, u32* __restrict_
     }
 }
 
+// first rows of P balanced slices: slice r starts at the row that holds link r * total / P
+__global__ void k_ws_bounds(const u32* __restrict__ ptr2, int n, int parts, int* __restrict__ bounds /* [parts + 1] */);
+
 // largest r in [0, n) with ptr2[r] <= q   (ptr2 strictly increasing: every row owns >= 1 link)
 __device__ __forceinline__ int ws_row_of(const u32* __restrict__ ptr2, int n, u32 q) {
     int lo = 0, hi = n;                       // invariant: ptr2[lo] <= q < ptr2[hi]  (ptr2[n] = total > q)
@@ -60,9 +64,10 @@ __device__ __forceinline__ int ws_row_of(const u32* __restrict__ ptr2, int n, u3
     return lo;
 }
 
+// The stream covers the links [q0, q0 + nnz2) of the whole-graph numbering (q0 > 0 for a row slice of a partitioned graph).
 __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                          const double* __restrict__ in_val, int n, u32 nnz2, size_t padded, int32_t* __restrict__ ws_src,
-                          double* __restrict__ ws_val /* may be null */) {
+                          const double* __restrict__ in_val, int n, u32 q0, u32 nnz2, size_t padded,
+                          int32_t* __restrict__ ws_src, double* __restrict__ ws_val /* may be null */) {
     const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (phys >= padded) return;
     // Inside a stage of WS_STAGE links the stream is stored lane-major: the int4 that lane L loads in round j (physical
@@ -75,8 +80,8 @@ __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ 
         if (ws_val) ws_val[phys] = 0.0;
         return;
     }
-    const int r = ws_row_of(ptr2, n, (u32)q);
-    const u32 j = (u32)q - ptr2[r];
+    const int r = ws_row_of(ptr2, n, q0 + (u32)q);
+    const u32 j = q0 + (u32)q - ptr2[r];
     const u32 b = in_ptr[r], deg = in_ptr[r + 1] - b;
     if (deg == 0) {
         ws_src[phys] = (int32_t)((u32)n | END_BIT);
@@ -87,13 +92,22 @@ __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ 
     }
 }
 
-__global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, int n_tiles, u32* __restrict__ ws_tile) {
+__global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, u32 q0, int row_end, int n_tiles, u32* __restrict__ ws_tile) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
-    if (t == n_tiles) { ws_tile[t] = (u32)n; return; }
-    const u32 q = (u32)t * (u32)WS_TILE;
+    if (t == n_tiles) { ws_tile[t] = (u32)row_end; return; }
+    const u32 q = q0 + (u32)t * (u32)WS_TILE;
     const int r = ws_row_of(ptr2, n, q);
     ws_tile[t] = (u32)r | (q > ptr2[r] ? END_BIT : 0u);
+}
+
+__global__ void k_ws_bounds(const u32* __restrict__ ptr2, int n, int parts, int* __restrict__ bounds) {
+    const int r = threadIdx.x;
+    if (r > parts) return;
+    if (r == 0) { bounds[0] = 0; return; }
+    if (r == parts) { bounds[r] = n; return; }
+    const u64 q = (u64)ptr2[n] * (u64)r / (u64)parts;
+    bounds[r] = ws_row_of(ptr2, n, (u32)q);
 }
 
 void stream_prepare(rwr_graph* g) {
@@ -118,6 +132,30 @@ void stream_prepare(rwr_graph* g) {
     CUDA_CHECK(cudaMemcpyAsync(&nnz2, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(ptr2.p + n, total.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
+    // row-partitioned graph: this rank keeps the rows [row_begin, row_end) of W^T, slices balanced by link count
+    u32 q0 = 0;
+    g->row_begin = 0;
+    g->row_end = n;
+    const int parts = dist_n_ranks(g->comm);
+    if (parts > 1) {
+        if (parts > 1023) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 1023 ranks");
+        DevBuf<int> bounds;
+        bounds.alloc((size_t)parts + 1);
+        k_ws_bounds<<<1, 1024, 0, st>>>(ptr2.p, n, parts, bounds.p);
+        KERNEL_CHECK();
+        g->part_rows.resize((size_t)parts + 1);
+        CUDA_CHECK(cudaMemcpyAsync(g->part_rows.data(), bounds.p, ((size_t)parts + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const int rank = dist_rank(g->comm);
+        g->row_begin = g->part_rows[rank];
+        g->row_end = g->part_rows[rank + 1];
+        u32 lim[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(&lim[0], ptr2.p + g->row_begin, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&lim[1], ptr2.p + g->row_end, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        q0 = lim[0];
+        nnz2 = lim[1] - lim[0];
+    }
     const int n_tiles = (int)(((u64)nnz2 + WS_TILE - 1) / WS_TILE);
     const size_t padded = (size_t)n_tiles * WS_TILE;
     g->ws_nnz = nnz2;
@@ -126,11 +164,16 @@ void stream_prepare(rwr_graph* g) {
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     if (valued) g->ws_val64.alloc(padded, &g->pool);
     g->ws_tile.alloc((size_t)n_tiles + 1, &g->pool);
-    k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, nnz2,
-                                                  padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
-    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, n_tiles, g->ws_tile.p);
+    if (padded)
+        k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, q0,
+                                                      nnz2, padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, g->ws_tile.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
+    if (parts > 1) {          // the whole-graph pull arrays are only needed by the batched path, which a slice does not run
+        g->in_src.release();
+        g->in_val64.release();
+    }
 }
 
 // Shared memory and L1 share the SM's 256 KB, and the L1 side is what holds the sectors of the gathers in flight: with
@@ -438,7 +481,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
     const T uni_add = (T)((p.seed < 0) ? S * p.inv_n : 0.0);
     const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
     double accS = 0.0, accR = 0.0;
-    for (int row = blockIdx.x * FIN_THREADS + threadIdx.x; row < p.n; row += gridDim.x * FIN_THREADS) {
+    for (int row = p.row_begin + blockIdx.x * FIN_THREADS + threadIdx.x; row < p.row_end; row += gridDim.x * FIN_THREADS) {
         T y = ld_stream(p.y + row, pol_first);
         const T invr = ld_stream(p.inv + row, pol_first);
         if (row == p.seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
@@ -486,7 +529,7 @@ int ws_main_grid(const rwr_graph* g) {
 }
 int ws_fix_grid(const rwr_graph* g) { return (int)div_up((size_t)std::max(g->ws_tiles, 1), FIX_THREADS); }
 int ws_fin_grid(const rwr_graph* g) {
-    return std::max(1, std::min(g->sm_count * 8, (int)div_up((size_t)std::max(g->n, 1), FIN_THREADS)));
+    return std::max(1, std::min(g->sm_count * 8, (int)div_up((size_t)std::max(g->row_end - g->row_begin, 1), FIN_THREADS)));
 }
 
 template <typename T>

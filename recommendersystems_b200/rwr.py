@@ -105,13 +105,44 @@ def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_w
                       hot_min_degree=int(hot_min_degree), reserved1=0)
 
 
+class Comm:
+    """NCCL communicator of the row-partitioned mode (include/rwr_b200.h `rwr_comm`): one per process / GPU."""
+
+    def __init__(self, rank: int, n_ranks: int, unique_id: bytes, device: int = -1):
+        if len(unique_id) != 128:
+            raise ValueError("unique_id must be the 128 bytes of Comm.unique_id()")
+        self._h = C.c_void_p()
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+        o = _opts(device=device)
+        buf = C.create_string_buffer(unique_id, 128)
+        _check(N.lib().rwr_comm_create(self.rank, self.n_ranks, buf, C.byref(o), C.byref(self._h)))
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        _check(N.lib().rwr_comm_unique_id(buf))
+        return buf.raw
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            N.lib().rwr_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Graph:
     """Graph.cs:37-94.  `nodes`: Dictionary<int, Node>; `edges`: Dictionary<int, List<ForwardLink>>."""
 
     def __init__(self, nodes: Optional[Dict[int, Node]] = None, edges: Optional[Dict[int, List[ForwardLink]]] = None,
-                 **opts):
+                 comm: Optional["Comm"] = None, **opts):
         self._h = C.c_void_p()
         self._opts = opts
+        self._comm = comm                 # row-partitioned over the ranks of `comm` (every rank passes the same input)
         self.nodes = nodes
         self.edges = edges
         if nodes is not None:
@@ -136,23 +167,30 @@ class Graph:
         if not (len(src) == len(dst) == len(etype) == len(w)) or len(node_id) != len(node_type):
             raise ValueError("array lengths differ")
         o = _opts(**self._opts)
+        if self._comm is not None:
+            _check(N.lib().rwr_graph_create_partitioned(len(node_id), _p(node_id), _p(node_type), len(src), _p(src), _p(dst),
+                                                        _p(etype), _p(w), C.byref(o), self._comm._h, C.byref(self._h)))
+            return
         _check(N.lib().rwr_graph_create(len(node_id), _p(node_id), _p(node_type), len(src), _p(src), _p(dst), _p(etype),
                                         _p(w), C.byref(o), C.byref(self._h)))
 
     @classmethod
-    def from_arrays(cls, node_id, node_type, src, dst, etype, w, **opts) -> "Graph":
+    def from_arrays(cls, node_id, node_type, src, dst, etype, w, comm: Optional["Comm"] = None, **opts) -> "Graph":
         """Flattened SoA form of (nodes, edges): links grouped by source in insertion order."""
-        g = cls(None, None, **opts)
+        g = cls(None, None, comm=comm, **opts)
         g._create(node_id, node_type, src, dst, etype, w)
         return g
 
     @classmethod
-    def synthetic(cls, spec: dict, **opts) -> "Graph":
+    def synthetic(cls, spec: dict, comm: Optional["Comm"] = None, **opts) -> "Graph":
         """Deterministic synthetic graph generated on the device (replaces DataLoader + SQLite)."""
-        g = cls(None, None, **opts)
+        g = cls(None, None, comm=comm, **opts)
         s = SynthSpec(spec).to_c()
         o = _opts(**opts)
-        _check(N.lib().rwr_synth_create(C.byref(s), C.byref(o), C.byref(g._h)))
+        if comm is not None:
+            _check(N.lib().rwr_synth_create_partitioned(C.byref(s), C.byref(o), comm._h, C.byref(g._h)))
+        else:
+            _check(N.lib().rwr_synth_create(C.byref(s), C.byref(o), C.byref(g._h)))
         return g
 
     def close(self):
