@@ -211,6 +211,10 @@ def run_ours(args):
         brec.RecommendationBatch(bseeds, C_FLOAT, N_ITER, TOP_K)
         torch.cuda.synchronize()
         batched[bname] = (time.perf_counter() - t0, brec.last_info.iterate_ms * 1e-3)
+    # ---- C4-style leg (N > 1 only): the SAME graph row-partitioned over the ranks, per-iteration allGather of x
+    parted = None
+    if dist is not None and not args.no_partitioned:
+        parted = partitioned_leg(rs, dist, torch, spec, rank, world, local, int(seeds[0]), c, precision, args.steps)
     clocks = sampler.stop()
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, iter_ms, batched["fp64"][0], batched["fp32"][0], batched["fp64"][1],
@@ -276,6 +280,7 @@ def run_ours(args):
                         "fp32": {"seeds_per_s": round(nb * world / b32_s, 1),
                                  "seed_gteps_e2e": round(nnz * N_ITER * nb * world / b32_s / 1e9, 1),
                                  "seed_gteps_iteration_loop": round(nnz * N_ITER * nb * world / b32_it / 1e9, 1)}},
+            "row_partitioned": parted,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -290,6 +295,44 @@ def run_ours(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precision, steps):
+    """One graph spread over the ranks (rows of W^T balanced by link count); every iteration allGathers x over NVLink.
+    Strong scaling of a single seed: GTEPS = nnz x iterations / time of the slowest rank."""
+    from recommendersystems_b200.rwr import run_fixed
+    uid = [rs.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = rs.Comm(rank, world, uid[0], device=local)
+    g = rs.Graph.synthetic(spec, comm=comm)
+    g.buildGraph()
+    info = g.info()
+    vb = 4 if precision == rs.FP32 else 8
+    m = run_fixed(g, [seed], c, N_ITER, precision)
+    m.rerun([seed], c, N_ITER)
+    dist.barrier()
+    torch.cuda.synchronize()
+    it_ms = 0.0
+    for _ in range(steps):
+        m.rerun([seed], c, N_ITER)
+        it_ms += m.info().iterate_ms
+    t = torch.tensor([it_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    it_ms = float(t)
+    top = m.topk(TOP_K)[0][0].tolist()
+    m.close()
+    g.close()
+    comm.close()
+    per_iter_ms = it_ms / steps / N_ITER
+    gathered = (world - 1) / world * info.n_nodes * vb          # bytes every rank receives per iteration
+    return {"workload": f"the C2 graph row-partitioned x{world} (strong scaling of one seed), ncclBroadcast-group allGather of x "
+                        f"+ 16-byte allReduce per iteration, 20 iterations",
+            "gteps": round(info.nnz * N_ITER * steps / (it_ms * 1e-3) / 1e9, 2), "ms_per_iteration": round(per_iter_ms, 4),
+            "rows_rank0": [info.row_begin, info.row_end],
+            "allgather_bytes_per_rank_per_iteration": int(gathered),
+            "nvlink": {"achieved_lower_bound": round(gathered / (per_iter_ms * 1e-3) / 1e9, 1), "peak": 900.0, "unit": "GB/s",
+                       "note": "bytes received per rank / whole iteration time (SpMV slice + exchange, not overlapped)"},
+            "top10_head": top[:3]}
 
 
 def cpu_baseline_leg(g, seed: int, nnz: int, sample_iters: int):
@@ -374,6 +417,7 @@ def main():
     ap.add_argument("--cpu-iters", type=int, default=2, help="iterations of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--batch-seeds", type=int, default=64, help="seeds per GPU of the batched (C3) leg")
+    ap.add_argument("--no-partitioned", action="store_true", help="skip the row-partitioned leg (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

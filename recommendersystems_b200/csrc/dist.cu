@@ -1,7 +1,8 @@
 // dist.cu -- K10: row-partitioned mode for one graph spread over several GPUs (no reference analogue).
 //
-// Every rank owns a contiguous block of rows of W^T (the destination nodes), balanced by link count, with its own
-// edge stream (stream.cu).  An iteration on a rank needs the whole gather vector x and produces the slice of the next
+// Every rank owns a contiguous block of rows of W^T (the destination nodes) with its own edge stream (stream.cu).  The
+// internal labels are dealt round-robin over the slices (graph.cu), so the blocks hold equal row counts and, every
+// P-th node of the degree order each, near-equal link counts: both the SpMV and the exchange are balanced.  An iteration on a rank needs the whole gather vector x and produces the slice of the next
 // one for its rows, so after every iteration the slices are allGathered over NVLink / NVSwitch (one grouped set of
 // in-place ncclBroadcast calls: slices have unequal lengths) and the two scalars every rank needs -- the restart mass S
 // and the L1 residual -- are summed with a 16-byte ncclAllReduce.  NCCL is bound at run time (dlopen) so that a
@@ -99,11 +100,81 @@ void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
 void dist_exchange(rwr_graph* g, void* x_next, size_t elt, double* two_doubles) {
     rwr_comm* c = g->comm;
     if (!c || c->n_ranks < 2) return;
-    dist_allgather_rows(g, x_next, elt);
+    if (x_next) dist_allgather_rows(g, x_next, elt);
     NCCL_CHECK(nccl().AllReduce(two_doubles, two_doubles, 2, ncclFloat64, ncclSum, c->comm, g->stream));
 }
 
 void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // synth.cu
+
+// Two persistent gather vectors per rank, mapped by every peer (one process per GPU -> CUDA IPC handles, exchanged
+// through the communicator itself).  RWR_DIST_NO_P2P=1, more than 8 ranks or a failing mapping fall back to NCCL.
+void dist_setup_p2p(rwr_graph* g) {
+    rwr_comm* c = g->comm;
+    g->p2p = false;
+    if (!c || c->n_ranks < 2 || c->n_ranks > 8 || getenv("RWR_DIST_NO_P2P")) return;
+    cudaStream_t st = g->stream;
+    const int P = c->n_ranks;
+    const size_t bytes = ((size_t)g->n + 8) * 8;
+    for (int b = 0; b < 2; b++) {
+        CUDA_CHECK(cudaMalloc(&g->px[b], bytes));
+        g->pool.bytes += (int64_t)bytes;
+        CUDA_CHECK(cudaMemsetAsync(g->px[b], 0, bytes, st));
+    }
+    // handles: [P][2] x 64 bytes, every rank broadcasts its own pair
+    DevBuf<unsigned char> hb;
+    hb.alloc((size_t)P * 128);
+    std::vector<unsigned char> host((size_t)P * 128, 0);
+    for (int b = 0; b < 2; b++) {
+        cudaIpcMemHandle_t h;
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, g->px[b]));
+        static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
+        memcpy(host.data() + (size_t)c->rank * 128 + b * 64, &h, 64);
+    }
+    CUDA_CHECK(cudaMemcpyAsync(hb.p, host.data(), host.size(), cudaMemcpyHostToDevice, st));
+    NcclApi& api = nccl();
+    NCCL_CHECK(api.GroupStart());
+    for (int r = 0; r < P; r++) NCCL_CHECK(api.Broadcast(hb.p + (size_t)r * 128, hb.p + (size_t)r * 128, 128, ncclInt8, r, c->comm, st));
+    NCCL_CHECK(api.GroupEnd());
+    CUDA_CHECK(cudaMemcpyAsync(host.data(), hb.p, host.size(), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    int ok = 1;
+    for (int b = 0; b < 2; b++) g->peer_px[b].assign(P, nullptr);
+    for (int r = 0; r < P && ok; r++) {
+        for (int b = 0; b < 2; b++) {
+            if (r == c->rank) { g->peer_px[b][r] = g->px[b]; continue; }
+            cudaIpcMemHandle_t h;
+            memcpy(&h, host.data() + (size_t)r * 128 + b * 64, 64);
+            if (cudaIpcOpenMemHandle(&g->peer_px[b][r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                g->peer_px[b][r] = nullptr;
+                ok = 0;
+                break;
+            }
+        }
+    }
+    // all ranks must agree: one failing mapping anywhere sends everybody to the NCCL path
+    DevBuf<double> flag;
+    flag.alloc(1);
+    const double mine = ok ? 0.0 : 1.0;
+    CUDA_CHECK(cudaMemcpyAsync(flag.p, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(api.AllReduce(flag.p, flag.p, 1, ncclFloat64, ncclSum, c->comm, st));
+    double bad = 0.0;
+    CUDA_CHECK(cudaMemcpyAsync(&bad, flag.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (bad != 0.0) { dist_release_p2p(g); return; }
+    g->p2p = true;
+}
+
+void dist_release_p2p(rwr_graph* g) {
+    const int me = dist_rank(g->comm);
+    for (int b = 0; b < 2; b++) {
+        for (int r = 0; r < (int)g->peer_px[b].size(); r++)
+            if (r != me && g->peer_px[b][r]) cudaIpcCloseMemHandle(g->peer_px[b][r]);
+        g->peer_px[b].clear();
+        if (g->px[b]) { cudaFree(g->px[b]); g->pool.bytes -= (int64_t)(((size_t)g->n + 8) * 8); g->px[b] = nullptr; }
+    }
+    g->p2p = false;
+}
 
 extern "C" {
 

@@ -11,6 +11,7 @@
 
 #include "graph.h"
 #include "primitives.cuh"
+#include "dist.h"
 
 // ------------------------------------------------------------------------------------------------ kernels
 __global__ void k_i32_to_u8(const int32_t* __restrict__ in, u8* __restrict__ out, size_t n, int* bad) {
@@ -216,6 +217,21 @@ __global__ void k_assign_cold(const u32* __restrict__ sorted_ids, u32 n_cold, u3
         new_of_old[o] = (int32_t)(n_hot + p);
         old_of_new[n_hot + p] = o;
     }
+}
+
+// Row-partitioned graphs: deal the label order (hot nodes by descending degree, then the clustered cold nodes) round-robin
+// to the P slices: position i goes to slice i mod P, at offset i / P.  Slice r holds q + (r < rem) labels (q = n / P,
+// rem = n mod P), so labels stay dense in [0, n).  Every contiguous slice then holds every P-th node of that order:
+// equal rows AND (statistically) equal link counts per rank, and the hottest nodes still come first in a slice.
+__global__ void k_interleave_labels(const int32_t* __restrict__ old_of_new_in, int32_t n, int32_t parts,
+                                    int32_t* __restrict__ old_of_new, int32_t* __restrict__ new_of_old) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int32_t q = n / parts, rem = n % parts, r = i % parts;
+    const int32_t lab = r * q + (r < rem ? r : rem) + i / parts;
+    const int32_t o = old_of_new_in[i];
+    old_of_new[lab] = o;
+    new_of_old[o] = lab;
 }
 
 __global__ void k_identity_perm(int32_t n, int32_t* a, int32_t* b) {
@@ -474,6 +490,23 @@ static void graph_build_impl(rwr_graph* g) {
         KERNEL_CHECK();
     }
 
+    // ---- row-partitioned graph: interleave the label order over the slices (see k_interleave_labels)
+    {
+        const int parts = dist_n_ranks(g->comm);
+        if (parts > 1 && n > 0) {
+            g->n_hot = n;                             // hotness is no longer a label prefix
+            DevBuf<int32_t> tmp;
+            tmp.alloc(n);
+            CUDA_CHECK(cudaMemcpyAsync(tmp.p, g->old_of_new.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+            k_interleave_labels<<<grid_for(n), 256, 0, st>>>(tmp.p, n, parts, g->old_of_new.p, g->new_of_old.p);
+            KERNEL_CHECK();
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            g->part_rows.resize((size_t)parts + 1);
+            const int32_t q = n / parts, rem = n % parts;
+            for (int r = 0; r <= parts; r++) g->part_rows[r] = r * q + std::min<int32_t>(r, rem);
+        }
+    }
+
     // ---- K5: transpose to the pull layout with a stable sort keyed by the (relabelled) target
     g->in_ptr.alloc((size_t)n + 1, &g->pool);
     g->in_src.alloc(nnz + IDX_PAD, &g->pool);
@@ -514,6 +547,7 @@ static void graph_build_impl(rwr_graph* g) {
     g->n_items = hs.n_items;
 
     iterate_prepare(g);
+    dist_setup_p2p(g);
 
     CUDA_CHECK(cudaEventRecord(ev1, st));
     CUDA_CHECK(cudaEventSynchronize(ev1));
@@ -703,6 +737,7 @@ void rwr_graph_destroy(rwr_graph* g) {
     if (!g) return;
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
+    dist_release_p2p(g);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }

@@ -78,6 +78,12 @@ struct rwr_graph {
     rwr_comm* comm = nullptr;
     int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
     std::vector<int> part_rows;           // [n_ranks + 1] first row of every rank's slice
+    // gather vectors of a partitioned graph live in two persistent buffers that every peer maps through CUDA IPC: the
+    // epilogue kernel stores a rank's slice of the next x straight into the peers' copies over NVLink (dist.cu)
+    bool p2p = false;
+    void* px[2] = {nullptr, nullptr};     // (n + 8) * 8 bytes each, cudaMalloc
+    std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
+
 
     float build_ms = 0.f, synth_ms = 0.f;
     int sm_count = 148;

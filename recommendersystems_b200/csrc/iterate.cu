@@ -682,9 +682,13 @@ __global__ void k_f64_to_f32(const double* __restrict__ in, float* __restrict__ 
     if (i < n) out[i] = (float)in[i];
 }
 
-// threshold mode on a row slice: the test of Model.cs:114 on the residual summed over all ranks
-__global__ void k_converged(IterCtl* ctl, double thr) {
-    if (!ctl->done && ctl->resid < thr) ctl->done = 1;
+// row slice: after the allReduce of ctl->red, the sums over all ranks become S and the residual; threshold mode then
+// applies the test of Model.cs:114.  A converged run ignores the (stale) sums of its no-op launches.
+__global__ void k_after_reduce(IterCtl* ctl, double thr, int use_thr) {
+    if (ctl->done) return;
+    ctl->S = ctl->red[0];
+    ctl->resid = ctl->red[1];
+    if (use_thr && ctl->red[1] < thr) ctl->done = 1;
 }
 
 template <typename T>
@@ -773,12 +777,12 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool write_y,
         const bool parted = dist_n_ranks(g->comm) > 1;
         // on a row slice the convergence test needs the residual of all slices: it runs after the exchange
         ws_launch_iteration<T>(g, p, resid, thr, parted ? 0 : use_thr);
-        if (parted) {
-            dist_exchange(g, p.x_next, sizeof(T), &p.ctl->S);        // IterCtl starts with { S, resid }
-            if (use_thr) {
-                k_converged<<<1, 1, 0, st>>>(p.ctl, thr);
-                KERNEL_CHECK();
-            }
+        static const bool skip_exchange = getenv("RWR_DIST_SKIP") != nullptr;      // timing probe only: wrong results
+        if (parted && !skip_exchange) {
+            // x_next: already in every peer's copy when the epilogue stored it there (p.n_peers > 0), else NCCL
+            dist_exchange(g, p.n_peers ? nullptr : p.x_next, sizeof(T), p.ctl->red);
+            k_after_reduce<<<1, 1, 0, st>>>(p.ctl, thr, use_thr);
+            KERNEL_CHECK();
         }
         return;
     }
@@ -804,7 +808,24 @@ struct RunWorkspace {
     Scratch<unsigned char> xa, xb, ya;
     Scratch<double> carry, head, slot_S, slot_R;
     Scratch<IterCtl> ctl;
+    void* x[2] = {nullptr, nullptr};      // the two gather vectors: scratch, or the peer-mapped buffers of a partitioned graph
+    void alloc_x(rwr_graph* g, size_t vec_bytes) {
+        if (g->p2p) { x[0] = g->px[0]; x[1] = g->px[1]; return; }
+        xa.alloc(&g->scratch, vec_bytes); xb.alloc(&g->scratch, vec_bytes);
+        x[0] = xa.p; x[1] = xb.p;
+    }
 };
+
+// peers' copies of the buffer `x_next` is (row-partitioned graphs with peer-mapped gather vectors)
+template <typename T>
+static void set_peers(rwr_graph* g, IterParams<T>& p, const void* x_next) {
+    p.parted = dist_n_ranks(g->comm) > 1;
+    p.n_peers = 0;
+    if (!g->p2p) return;
+    const int b = (x_next == g->px[0]) ? 0 : 1, me = dist_rank(g->comm);
+    for (int r = 0; r < (int)g->peer_px[b].size(); r++)
+        if (r != me) p.peer_next[p.n_peers++] = g->peer_px[b][r];
+}
 
 // Runs one seed.  mode 0: fixed n_iter; mode 1: threshold.  Final rank lands in y_out (internal labels).
 template <typename T>
@@ -823,8 +844,8 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     const int hub = hub_entries_for(g, Prec<T>::id);
     const size_t smem = smem_fixed_bytes(sizeof(T)) + (size_t)hub * sizeof(T);
 
-    T* xa = reinterpret_cast<T*>(ws.xa.p);
-    T* xb = reinterpret_cast<T*>(ws.xb.p);
+    T* xa = reinterpret_cast<T*>(ws.x[0]);
+    T* xb = reinterpret_cast<T*>(ws.x[1]);
     T* ya = reinterpret_cast<T*>(ws.ya.p);
     IterParams<T> p;
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
@@ -852,6 +873,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     if (mode == 0) {
         for (int it = 0; it < n_iter; it++) {
             p.x = x_cur; p.x_next = x_nxt; p.r_prev = nullptr; p.y = y_out;
+            set_peers<T>(g, p, x_nxt);
             launch_iteration<T>(g, p, /*write_y=*/it == n_iter - 1, /*resid=*/false, main_grid, fix_grid, smem, 0.0, 0);
             std::swap(x_cur, x_nxt);
             launched++;
@@ -868,6 +890,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
                 if (max_iter > 0 && launched >= max_iter) break;
                 T* target = (r_cur == ya) ? y_out : ya;
                 p.x = x_cur; p.x_next = x_nxt; p.r_prev = r_cur; p.y = target;
+                set_peers<T>(g, p, x_nxt);
                 launch_iteration<T>(g, p, true, true, main_grid, fix_grid, smem, thr, 1);
                 std::swap(x_cur, x_nxt);
                 r_cur = target;
@@ -902,9 +925,7 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
         Prec<T>::ybuf(res).alloc(std::max<size_t>(1, ld * (size_t)n_seeds), nullptr);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
-    CUDA_CHECK(cudaMemsetAsync(ws.xa.p, 0, vec_bytes, st));
-    CUDA_CHECK(cudaMemsetAsync(ws.xb.p, 0, vec_bytes, st));
+    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
@@ -943,9 +964,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
-    CUDA_CHECK(cudaMemsetAsync(ws.xa.p, 0, vec_bytes, st));
-    CUDA_CHECK(cudaMemsetAsync(ws.xb.p, 0, vec_bytes, st));
+    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, (size_t)g->n_chunks * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, (size_t)g->n_chunks * sizeof(double), st));
@@ -962,8 +981,8 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     const int fix_grid = div_up((size_t)g->n_chunks, FIX_THREADS);
     const int hub = hub_entries_for(g, Prec<T>::id);
     const size_t smem = smem_fixed_bytes(sizeof(T)) + (size_t)hub * sizeof(T);
-    T* xa = reinterpret_cast<T*>(ws.xa.p);
-    T* xb = reinterpret_cast<T*>(ws.xb.p);
+    T* xa = reinterpret_cast<T*>(ws.x[0]);
+    T* xb = reinterpret_cast<T*>(ws.x[1]);
     T* ya = reinterpret_cast<T*>(ws.ya.p);
     IterParams<T> p;
     p.in_ptr = g->in_ptr.p; p.in_src = g->in_src.p; p.in_val = Prec<T>::val(g); p.part = g->part.p;
@@ -983,6 +1002,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     T* x_nxt = xb;
     for (int it = 0; it < 3 + reps; it++) {
         p.x = x_cur; p.x_next = x_nxt;
+        set_peers<T>(g, p, x_nxt);
         const int r = it - 3;
         if (r >= 0) CUDA_CHECK(cudaEventRecord(ev[3 * r], st));
         if (g->opts.kernel == 0) ws_launch_spmv_only<T>(g, p);
@@ -1018,7 +1038,7 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.xa.alloc(&g->scratch, vec_bytes); ws.xb.alloc(&g->scratch, vec_bytes); ws.ya.alloc(&g->scratch, 16);
+    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, 16);
     ws.carry.alloc(&g->scratch, (size_t)g->n_chunks); ws.head.alloc(&g->scratch, (size_t)g->n_chunks);
     const size_t slots = (size_t)g->sm_count * 8 + div_up((size_t)g->n_chunks, FIX_THREADS) + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);

@@ -24,6 +24,9 @@ struct IterParams {
     const u32* ws_tile;     // [ws_tiles + 1] first row of a tile | continued-row flag in bit 31
     int ws_tiles;
     int row_begin, row_end; // rows of W^T this rank owns ([0, n) unless the graph is row-partitioned)
+    int parted;             // row-partitioned: the epilogue leaves its partial sums in ctl->red for the allReduce
+    int n_peers;            // peers whose copy of x_next the epilogue writes directly (NVLink peer stores)
+    void* peer_next[7];
     const T* x;             // gather source, internal labels
     const T* inv;
     const T* r_prev;        // previous rank (residual)

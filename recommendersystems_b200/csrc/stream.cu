@@ -51,9 +51,6 @@ __global__ void k_ws_len(const u32* __restrict__ in_ptr, int n, u32* __restrict_
     }
 }
 
-// first rows of P balanced slices: slice r starts at the row that holds link r * total / P
-__global__ void k_ws_bounds(const u32* __restrict__ ptr2, int n, int parts, int* __restrict__ bounds /* [parts + 1] */);
-
 // largest r in [0, n) with ptr2[r] <= q   (ptr2 strictly increasing: every row owns >= 1 link)
 __device__ __forceinline__ int ws_row_of(const u32* __restrict__ ptr2, int n, u32 q) {
     int lo = 0, hi = n;                       // invariant: ptr2[lo] <= q < ptr2[hi]  (ptr2[n] = total > q)
@@ -101,15 +98,6 @@ __global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, u32 q0, int row_
     ws_tile[t] = (u32)r | (q > ptr2[r] ? END_BIT : 0u);
 }
 
-__global__ void k_ws_bounds(const u32* __restrict__ ptr2, int n, int parts, int* __restrict__ bounds) {
-    const int r = threadIdx.x;
-    if (r > parts) return;
-    if (r == 0) { bounds[0] = 0; return; }
-    if (r == parts) { bounds[r] = n; return; }
-    const u64 q = (u64)ptr2[n] * (u64)r / (u64)parts;
-    bounds[r] = ws_row_of(ptr2, n, (u32)q);
-}
-
 void stream_prepare(rwr_graph* g) {
     cudaStream_t st = g->stream;
     const int n = g->n;
@@ -132,20 +120,12 @@ void stream_prepare(rwr_graph* g) {
     CUDA_CHECK(cudaMemcpyAsync(&nnz2, total.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(ptr2.p + n, total.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    // row-partitioned graph: this rank keeps the rows [row_begin, row_end) of W^T, slices balanced by link count
+    // row-partitioned graph: this rank keeps the rows [row_begin, row_end) of W^T
     u32 q0 = 0;
     g->row_begin = 0;
     g->row_end = n;
     const int parts = dist_n_ranks(g->comm);
-    if (parts > 1) {
-        if (parts > 1023) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 1023 ranks");
-        DevBuf<int> bounds;
-        bounds.alloc((size_t)parts + 1);
-        k_ws_bounds<<<1, 1024, 0, st>>>(ptr2.p, n, parts, bounds.p);
-        KERNEL_CHECK();
-        g->part_rows.resize((size_t)parts + 1);
-        CUDA_CHECK(cudaMemcpyAsync(g->part_rows.data(), bounds.p, ((size_t)parts + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_CHECK(cudaStreamSynchronize(st));
+    if (parts > 1) {                            // slices of equal row counts: graph.cu interleaved the labels for this
         const int rank = dist_rank(g->comm);
         g->row_begin = g->part_rows[rank];
         g->row_end = g->part_rows[rank + 1];
@@ -488,13 +468,19 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
         if (p.seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
         const T rw = mul_rn(p.omc, y);
         // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
-        st_policy(p.x_next + row, mul_rn(rw, invr), row < p.n_hot ? pol_last : pol_first);
+        const T xn = mul_rn(rw, invr);
+        st_policy(p.x_next + row, xn, row < p.n_hot ? pol_last : pol_first);
+        // row-partitioned: this rank's slice of the next x goes straight into every peer's copy (coalesced NVLink
+        // stores, overlapped with the rest of this kernel) -- the allGather is fused into the epilogue
+#pragma unroll 1
+        for (int j = 0; j < p.n_peers; j++) reinterpret_cast<T*>(p.peer_next[j])[row] = xn;
         accS += (invr == (T)0) ? (double)y : (double)sub_rn(y, rw);
         if (RESID) {
             const T rp = ld_stream(p.r_prev + row, pol_first);
             accR += (double)((rp > y) ? sub_rn(rp, y) : sub_rn(y, rp));
         }
     }
+    if (p.n_peers) __threadfence_system();                 // peer stores are visible before this kernel is seen complete
     block_sum2<FIN_THREADS>(accS, accR, scratch);
     if (threadIdx.x == 0) {
         p.slot_S[blockIdx.x] = accS;
@@ -514,11 +500,16 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
         __syncthreads();
         block_sum2<FIN_THREADS>(a, b, scratch);
         if (threadIdx.x == 0) {
-            ctl->S = a;
-            ctl->resid = b;
             ctl->iters += 1;
             ctl->ticket = 0;
-            if (use_thr && b < thr) ctl->done = 1;        // strict `<` (Model.cs:114)
+            if (p.parted) {                               // partial sums of this rank's rows: k_after_reduce finishes the job
+                ctl->red[0] = a;
+                ctl->red[1] = b;
+            } else {
+                ctl->S = a;
+                ctl->resid = b;
+                if (use_thr && b < thr) ctl->done = 1;    // strict `<` (Model.cs:114)
+            }
         }
     }
 }
