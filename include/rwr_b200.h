@@ -65,7 +65,7 @@ typedef struct rwr_opts {
     int32_t batch_width;   /* seed columns per SpMM tile; 0 = auto                                              */
     int32_t kernel;        /* SpMV kernel: 0 = warp-streamed edge stream (default); 1 = pipelined producer/consumer; 2 = phased */
     uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
-    int32_t hot_min_degree;/* nodes with fewer explicit links are clustered by first neighbour; 0 = auto (2), 1 = off */
+    int32_t hot_min_degree;/* nodes with fewer explicit links are clustered by first neighbour; 0 = auto (8), 1 = off */
     int32_t reserved1;
 } rwr_opts;
 

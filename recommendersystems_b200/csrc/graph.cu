@@ -460,7 +460,7 @@ static void graph_build_impl(rwr_graph* g) {
         bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, n, ceil_log2_u64((u64)hs.max_out + 1), st, &g->pool);
         k_invert_perm<<<grid_for(n), 256, 0, st>>>(fl ? v1.p : v0.p, n, g->old_of_new.p, g->new_of_old.p);
         KERNEL_CHECK();
-        const u32 hot_min = g->opts.hot_min_degree > 0 ? (u32)g->opts.hot_min_degree : 2u;
+        const u32 hot_min = g->opts.hot_min_degree > 0 ? (u32)g->opts.hot_min_degree : 8u;   // profiles/microbench/hotmin_sweep.py
         if (hot_min > 1) {
             DevBuf<u32> counts, pos, total;
             counts.alloc(2); pos.alloc(n); total.alloc(1);
