@@ -85,7 +85,6 @@ struct rwr_graph {
     std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
 
 
-    int64_t l2_persist_bytes = -1;        // persisting-L2 window budget of this handle's stream (-1: not queried yet)
     float build_ms = 0.f, synth_ms = 0.f;
     int sm_count = 148;
     int max_smem_optin = 0;

@@ -411,35 +411,6 @@ template <> struct PrecMM<float> {
 
 void ensure_fp32_arrays(rwr_graph* g);    // iterate.cu
 
-// ---- persisting-L2 window (cudaStreamAttributeAccessPolicyWindow) on the handle's stream
-static bool l2_window_prepare(rwr_graph* g) {
-    if (g->l2_persist_bytes < 0) {
-        int max_persist = 0, max_window = 0;
-        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, g->device);
-        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, g->device);
-        size_t want = std::min<size_t>((size_t)max_persist, (size_t)64 << 20);
-        if (want == 0 || max_window == 0 || cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
-            cudaGetLastError();
-            g->l2_persist_bytes = 0;
-        } else {
-            g->l2_persist_bytes = (int64_t)std::min<size_t>(want, (size_t)max_window);
-        }
-        if (getenv("RWR_DEBUG_L2")) fprintf(stderr, "[rwr] persisting L2: max %d B, max window %d B -> budget %lld B\n", max_persist, max_window, (long long)g->l2_persist_bytes);
-    }
-    return g->l2_persist_bytes > 0;
-}
-static void l2_window_set(rwr_graph* g, const void* base, size_t bytes) {
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
-    attr.accessPolicyWindow.num_bytes = std::min<size_t>(bytes, (size_t)g->l2_persist_bytes);
-    attr.accessPolicyWindow.hitRatio = 1.0f;
-    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(g->stream, cudaStreamAttributeAccessPolicyWindow, &attr) != cudaSuccess) cudaGetLastError();
-    if (!base) cudaCtxResetPersistingL2Cache();
-}
-
 template <typename T>
 struct SpmmWorkspace {
     Scratch<T> xa, xb;
@@ -491,12 +462,8 @@ void spmm_run_tile(rwr_graph* g, const int* seeds_int, int n_active, double c, i
     *launches += 2;
     T* x_cur = ws.xa.p;
     T* x_nxt = ws.xb.p;
-    // L2 residency of the hot source rows: a persisting access-policy window over the head of the matrix being gathered
-    // (rows are ordered by descending out-degree, so the first n_keep rows receive most of the gathers)
-    const bool use_window = l2_window_prepare(g) && !getenv("RWR_NO_L2_WINDOW");
     for (int it = 0; it < n_iter; it++) {
         p.x = x_cur; p.x_next = x_nxt; p.y = y_out;
-        if (use_window) l2_window_set(g, x_cur, (size_t)p.n_keep * B * sizeof(T));
         const bool last = it == n_iter - 1;
 #define MM_LAUNCH(V, W)                                                                                         \
     do {                                                                                                        \
@@ -512,7 +479,6 @@ void spmm_run_tile(rwr_graph* g, const int* seeds_int, int n_active, double c, i
         *launches += 2;
         std::swap(x_cur, x_nxt);
     }
-    if (use_window) l2_window_set(g, nullptr, 0);
     CUDA_CHECK(cudaStreamSynchronize(st));      // the workspace goes back to the handle's scratch pool on return
 }
 
