@@ -88,21 +88,65 @@ __device__ void block_extract(Cand (&list)[TOPK_MAX], int k, Cand* out, Cand* sm
     }
 }
 
+// Pass 1 of the top-k: the best candidate key of every block's share.  The k-th largest of these block maxima is a
+// lower bound of the k-th best score overall (k distinct candidates reach it), so pass 2 only has to look at the few
+// candidates at or above it -- exact, and on the skewed score vectors of a random walk it skips almost everything.
+constexpr int TOPK_MAX_GRID = 1024;
+template <typename T>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_bound(const T* __restrict__ y, int ld, const u8* __restrict__ type_int,
+                                                             const u32* __restrict__ excl, int n, u64* __restrict__ block_max) {
+    __shared__ u64 sm[TOPK_THREADS / 32];
+    u64 best = 0;
+    for (int j = blockIdx.x * TOPK_THREADS + threadIdx.x; j < n; j += gridDim.x * TOPK_THREADS) {
+        if (type_int[j] != RWR_NODE_ITEM) continue;
+        if ((excl[j >> 5] >> (j & 31)) & 1u) continue;
+        const u64 key = score_key((double)y[(size_t)j * ld]);
+        best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, best, o); best = t > best ? t : best; }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = best;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < TOPK_THREADS / 32; w++) best = sm[w] > best ? sm[w] : best;
+        block_max[blockIdx.x] = best;
+    }
+}
+
 // y is read with a stride of `ld` elements: ld == 1 for one rank vector, ld == B for a column of a row-major tile
 template <typename T>
 __global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan(const T* __restrict__ y, int ld, const u8* __restrict__ type_int,
                                                             const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
-                                                            int n, int k, Cand* __restrict__ block_out) {
+                                                            int n, int k, const u64* __restrict__ block_max,
+                                                            Cand* __restrict__ block_out) {
     __shared__ Cand sm_best[TOPK_THREADS / 32];
     __shared__ int sm_owner[TOPK_THREADS / 32 + 1];
+    __shared__ u64 sm_max[TOPK_MAX_GRID];
+    __shared__ u64 sm_bound;
+    // the k-th largest block maximum (rank counting, ties by index); 0 == no bound when there are fewer than k blocks
+    const int nb = (int)gridDim.x;
+    for (int i = threadIdx.x; i < nb; i += TOPK_THREADS) sm_max[i] = block_max[i];
+    if (threadIdx.x == 0) sm_bound = 0;
+    __syncthreads();
+    if (nb >= k) {
+        for (int i = threadIdx.x; i < nb; i += TOPK_THREADS) {
+            const u64 v = sm_max[i];
+            int rank = 0;
+            for (int j = 0; j < nb; j++) rank += (sm_max[j] > v) || (sm_max[j] == v && j < i);
+            if (rank == k - 1) sm_bound = v;
+        }
+    }
+    __syncthreads();
+    const u64 bound = sm_bound;
     Cand list[TOPK_MAX];
 #pragma unroll
     for (int i = 0; i < TOPK_MAX; i++) { list[i].key = 0; list[i].id = 0; list[i].idx = -1; }
     for (int j = blockIdx.x * TOPK_THREADS + threadIdx.x; j < n; j += gridDim.x * TOPK_THREADS) {
         if (type_int[j] != RWR_NODE_ITEM) continue;
-        if ((excl[j >> 5] >> (j & 31)) & 1u) continue;
         Cand c;
         c.key = score_key((double)y[(size_t)j * ld]);
+        if (c.key < bound) continue;
+        if ((excl[j >> 5] >> (j & 31)) & 1u) continue;
         c.idx = j;
         const Cand& worst = list[TOPK_MAX - 1];
         if (worst.idx >= 0 && c.key < worst.key) continue;       // cheap reject before touching the id
@@ -226,10 +270,14 @@ template <typename T>
 static void topk_one(rwr_graph* g, const T* y, int ld, int seed, int k, u32* excl, size_t words, Cand* block_out, int grid,
                      int64_t* d_ids, double* d_scores, int* d_count) {
     mark_excluded(g, seed, excl, words);
-    k_topk_scan<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, ld, g->node_type_int.p, g->node_id_int.p, excl, g->n, k, block_out);
+    Scratch<u64> block_max;
+    block_max.alloc(&g->scratch, (size_t)grid);
+    k_topk_bound<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, ld, g->node_type_int.p, excl, g->n, block_max.p);
+    k_topk_scan<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, ld, g->node_type_int.p, g->node_id_int.p, excl, g->n, k, block_max.p,
+                                                         block_out);
     k_topk_merge<T><<<1, TOPK_THREADS, 0, g->stream>>>(block_out, grid * k, k, y, ld, d_ids, d_scores, d_count);
     KERNEL_CHECK();
-    g->pool.launches += 2;
+    g->pool.launches += 3;
 }
 
 static void ensure_items_by_id(rwr_graph* g) {
@@ -316,7 +364,7 @@ int rwr_topk(rwr_result* r, int32_t k, int64_t* out_ids, double* out_scores, int
         return RWR_OK;
     }
     const size_t words = ((size_t)g->n + 31) / 32 + 1;
-    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up((size_t)std::max(g->n, 1), TOPK_THREADS)));
+    const int grid = std::max(1, std::min(std::min(g->sm_count * 4, TOPK_MAX_GRID), (int)div_up((size_t)std::max(g->n, 1), TOPK_THREADS)));
     Scratch<u32> excl;
     Scratch<Cand> block_out;
     Scratch<int64_t> d_ids;
@@ -377,7 +425,7 @@ static void recommend_singles(rwr_graph* g, const int32_t* seeds, int n_seeds, d
     Scratch<T> y;
     y.alloc(&g->scratch, n + 8);
     const size_t words = (n + 31) / 32 + 1;
-    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
+    const int grid = std::max(1, std::min(std::min(g->sm_count * 4, TOPK_MAX_GRID), (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
     Scratch<u32> excl;
     Scratch<Cand> block_out;
     Scratch<int64_t> d_ids;
@@ -433,7 +481,7 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
     Scratch<T> y;
     y.alloc(&g->scratch, n * B + 16);
     const size_t words = (n + 31) / 32 + 1;
-    const int grid = std::max(1, std::min(g->sm_count * 4, (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
+    const int grid = std::max(1, std::min(std::min(g->sm_count * 4, TOPK_MAX_GRID), (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
     Scratch<u32> excl;
     Scratch<Cand> block_out;
     Scratch<int64_t> d_ids;
