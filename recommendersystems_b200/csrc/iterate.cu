@@ -652,6 +652,7 @@ __global__ void k_init(int n, int seed, T omc, const T* __restrict__ inv, T* __r
     if (j < 8) { x0[n + j] = (T)0; x1[n + j] = (T)0; }     // x[n] is the always-zero entry the edge stream pads with
     if (j == 0) {
         ctl->resid = 0.0; ctl->seed_sum = 0.0; ctl->seed_flag = 0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0;
+        ctl->tile_ctr = 0;
         if (seed < 0) ctl->S = S_uniform;
     }
     if (j >= n) return;

@@ -11,6 +11,7 @@ struct IterCtl {
     int done;          // threshold mode: converged, later launches are no-ops
     int iters;         // deliverRanks() calls performed
     unsigned ticket;
+    unsigned tile_ctr;  // k_spmv_ws: next tile to hand out (reset by k_finish_ws)
     double red[2];     // row-partitioned graphs: this rank's {restart mass, residual} partials, summed over the ranks in place
 };
 

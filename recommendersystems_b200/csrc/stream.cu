@@ -329,29 +329,36 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p
     }
     const u64 pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
-    const int gw = blockIdx.x * WS_WARPS + warp, GW = gridDim.x * WS_WARPS;
-    const int my_tiles = p.ws_tiles > gw ? (p.ws_tiles - gw + GW - 1) / GW : 0;
-    const int total = my_tiles * WS_SPT;       // stages of this warp (always even: WS_SPT is)
-    // link offset of this lane's first int4 in stage k of this warp's sequence (stages past the end re-read the last)
-    auto pos_of = [&](int k) -> size_t {
-        k = k < total ? k : total - 1;
-        return ((size_t)(gw + (k / WS_SPT) * GW) * WS_TILE) + (size_t)((k & (WS_SPT - 1)) * WS_STAGE + lane * 4);
+    // Tiles are handed out dynamically (one atomic per 8192 links, fetched a whole tile before it is needed): warps that
+    // draw cheap tiles (long rows, hub hits) simply take more of them, and the hand-out order keeps the stream walk ascending.
+    const int n_tiles = p.ws_tiles;
+    u32 grab = 0;                                  // lane 0: the tile drawn most recently (its value is only read a tile later)
+    if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+    int cur = (int)__shfl_sync(0xffffffffu, grab, 0);
+    if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+    int nxt = (int)__shfl_sync(0xffffffffu, grab, 0);
+    if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+    // link offset of this lane's first int4 in stage st of tile t (tiles past the end re-read the last one)
+    auto pos_of = [&](int t, int st) -> size_t {
+        t = t < n_tiles ? t : n_tiles - 1;
+        return (size_t)t * WS_TILE + (size_t)(st * WS_STAGE + lane * 4);
     };
 
-    if (total > 0) {
+    if (cur < n_tiles) {
         const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
         // two register stages, A and B, used alternately (the loop is unrolled by two so that no register that is the
         // target of a load in flight is ever copied): while stage X is being summed, the gathers of stage Y are in
         // flight and the indices of the stage after that are on their way into X's index registers.
         int4 ivA[WS_R], ivB[WS_R];
         T gA[WS_R][4], gB[WS_R][4], wA[WS_R][4], wB[WS_R][4];
-        size_t posA = pos_of(0), posB = pos_of(1);
+        size_t posA = pos_of(cur, 0), posB = pos_of(cur, 1);
 #pragma unroll
         for (int j = 0; j < WS_R; j++) {
             ivA[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + posA + j * WS_STEP), pol_stream);
             ivB[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + posB + j * WS_STEP), pol_stream);
         }
-        u32 meta_next = p.ws_tile[gw];
+        u32 meta_cur = p.ws_tile[cur];
+        u32 meta_nxt = p.ws_tile[nxt < n_tiles ? nxt : n_tiles];
         if (p.hub > 0) mbar_wait_a(smem0, 0);
         ws_gather_stage<T>(p, ivA, hub_gen, hub_addr, pol_keep, pol_stream, gA);
         if (VALUED) {
@@ -370,7 +377,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p
 #define WCLK_LAND_G(GX)
 #endif
         WCLK_DECL;
-#define WS_HALF(K, IVX, GX, WX, POSX, IVY, GY, WY, POSY)                                                               \
+        // ST: stage of tile `cur` in X; stage ST + 1 sits in Y; the indices of stage ST + 2 (of `cur`, or of `nxt`) go to X
+#define WS_HALF(ST, IVX, GX, WX, POSX, IVY, GY, WY, POSY)                                                              \
     {                                                                                                                  \
         const u32 fl = ((u32)IVX[0].x >> 31) | (((u32)IVX[0].y >> 31) << 1) | (((u32)IVX[0].z >> 31) << 2) |           \
                        (((u32)IVX[0].w >> 31) << 3) | (((u32)IVX[1].x >> 31) << 4) | (((u32)IVX[1].y >> 31) << 5) |    \
@@ -383,22 +391,19 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p
             _Pragma("unroll") for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + POSY + j * WS_STEP, pol_stream, WY[j]); \
         }                                                                                                              \
         WCLK(1);                                                                                                       \
-        POSX = pos_of((K) + 2);                                                                                        \
+        POSX = ((ST) + 2 < WS_SPT) ? pos_of(cur, (ST) + 2) : pos_of(nxt, (ST) + 2 - WS_SPT);                           \
         _Pragma("unroll") for (int j = 0; j < WS_R; j++)                                                               \
             IVX[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + POSX + j * WS_STEP), pol_stream);         \
         WCLK(2);                                                                                                       \
         WCLK_LAND_G(GX)                                                                                                \
         WCLK(3);                                                                                                       \
-        const int st = (K) & (WS_SPT - 1);                                                                             \
-        if (st == 0) {                                                                                                 \
-            s.tile = gw + ((K) / WS_SPT) * GW;                                                                         \
-            s.first_row = (int)(meta_next & 0x7fffffffu);                                                              \
-            s.cont = (meta_next >> 31) != 0;                                                                           \
+        if ((ST) == 0) {                                                                                               \
+            s.tile = cur;                                                                                              \
+            s.first_row = (int)(meta_cur & 0x7fffffffu);                                                               \
+            s.cont = (meta_cur >> 31) != 0;                                                                            \
             s.row_base = s.first_row;                                                                                  \
             s.lane_acc = 0.0;                                                                                          \
             s.spread = false;                                                                                          \
-            const int nt = s.tile + GW;                                                                                \
-            meta_next = p.ws_tile[nt < p.ws_tiles ? nt : p.ws_tiles];                                                  \
         }                                                                                                              \
         {                                                                                                              \
             double v[8];                                                                                               \
@@ -408,16 +413,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p
             ws_consume<T>(p, s, fl, v, lane, lt, le, pol_stream);                                                      \
         }                                                                                                              \
         WCLK(4);                                                                                                       \
-        if (st == WS_SPT - 1) {                                                                                        \
+        if ((ST) == WS_SPT - 1) {                                                                                      \
             const double c = s.spread ? warp_sum(s.lane_acc) : __shfl_sync(0xffffffffu, s.lane_acc, 31);               \
             if (lane == 0) p.carry[s.tile] = c;                                                                        \
         }                                                                                                              \
         WCLK(5);                                                                                                       \
     }
 
-        for (int k = 0; k < total; k += 2) {
-            WS_HALF(k, ivA, gA, wA, posA, ivB, gB, wB, posB)
-            WS_HALF(k + 1, ivB, gB, wB, posB, ivA, gA, wA, posA)
+        while (cur < n_tiles) {
+            for (int st = 0; st < WS_SPT; st += 2) {
+                WS_HALF(st, ivA, gA, wA, posA, ivB, gB, wB, posB)
+                WS_HALF(st + 1, ivB, gB, wB, posB, ivA, gA, wA, posA)
+            }
+            // next tile: the one drawn a tile ago becomes `nxt`, and a new one is drawn for later
+            cur = nxt;
+            meta_cur = meta_nxt;
+            nxt = (int)__shfl_sync(0xffffffffu, grab, 0);
+            if (lane == 0 && nxt < n_tiles) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+            meta_nxt = p.ws_tile[nxt < n_tiles ? nxt : n_tiles];
         }
 #undef WS_HALF
         WCLK_FLUSH;
@@ -502,6 +515,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
         if (threadIdx.x == 0) {
             ctl->iters += 1;
             ctl->ticket = 0;
+            ctl->tile_ctr = 0;                            // the next k_spmv_ws hands its tiles out from the start
             if (p.parted) {                               // partial sums of this rank's rows: k_after_reduce finishes the job
                 ctl->red[0] = a;
                 ctl->red[1] = b;
