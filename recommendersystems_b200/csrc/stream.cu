@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) k_spmv_ws(const IterParams<T> p
     }
     const u64 pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
 
-    // Tiles are handed out dynamically (one atomic per 8192 links, fetched a whole tile before it is needed): warps that
+    // Tiles are handed out dynamically (one atomic per tile, fetched a whole tile before it is needed): warps that
     // draw cheap tiles (long rows, hub hits) simply take more of them, and the hand-out order keeps the stream walk ascending.
     const int n_tiles = p.ws_tiles;
     u32 grab = 0;                                  // lane 0: the tile drawn most recently (its value is only read a tile later)

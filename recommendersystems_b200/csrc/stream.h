@@ -8,7 +8,7 @@ constexpr int WS_THREADS = WS_WARPS * 32;        // 512
 constexpr int WS_STEP = 128;                     // links per warp step: one int4 of indices per lane
 constexpr int WS_R = 2;                          // rounds per pipeline stage
 constexpr int WS_STAGE = WS_R * WS_STEP;         // 256 links per stage
-constexpr int WS_TILE = 8192;                    // links per tile (unit of work distribution and of the fix-up)
+constexpr int WS_TILE = 4096;                    // links per tile (unit of work distribution and of the fix-up)
 constexpr int WS_SPT = WS_TILE / WS_STAGE;       // 32 stages per tile
 constexpr int WS_HDR = 128;                      // mbarrier, ahead of the hub table
 constexpr int FIN_THREADS = 256;

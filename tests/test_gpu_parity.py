@@ -463,7 +463,7 @@ def test_rerun_reuses_the_model_and_matches_a_fresh_run(prec):
 
 def test_rows_without_in_links_and_tile_cuts():
     """Edge-stream corner cases: rows with no in-links (padding link to the zero entry), a hub row spanning several
-    8192-link tiles, rows ending exactly on a tile boundary; seeds inside each kind of row."""
+    4096-link tiles, rows ending exactly on a tile boundary; seeds inside each kind of row."""
     rng = np.random.default_rng(5)
     n = 30_000
     hub = 7
