@@ -39,6 +39,12 @@ C2_SPEC = dict(seed=20260102, n_users=1_000_000, n_items=10_000_000, n_third=0, 
                p1_byte=61, reserved=0)
 
 
+# C4 (BASELINE configs[3]): 5 M users + 45 M tweets, 45 M authorship + 700 M like + 200 M friendship relations -> ~1.8 B links
+C4_SPEC = dict(seed=20260104, n_users=5_000_000, n_items=45_000_000, n_third=0, authorship_per_mille=1000,
+               n_like=700_000_000, n_friend=200_000_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
+               p1_byte=61, reserved=0)
+
+
 def scaled_spec(scale: float) -> dict:
     s = dict(C2_SPEC)
     if scale != 1.0:
@@ -217,6 +223,8 @@ def run_ours(args):
         # the graph grows with the rank count (C2 x world/2: 205 M links at 2 ranks, 820 M at 8) so that a slice stays
         # C2-sized work, the regime the mode exists for (C4: a graph too large for one GPU)
         pspec = scaled_spec(args.scale * max(1.0, world / 2.0))
+        if world >= 8 and args.scale == 1.0:
+            pspec = dict(C4_SPEC)                       # BASELINE configs[3]: 50 M nodes, ~2 B links
         parted = partitioned_leg(rs, dist, torch, pspec, rank, world, local, int(seeds[0]), c, precision, args.steps)
     clocks = sampler.stop()
 
@@ -328,6 +336,9 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
     comm.close()
     per_iter_ms = it_ms / steps / N_ITER
     gathered = (world - 1) / world * info.n_nodes * vb          # bytes every rank receives per iteration
+    # SURVEY 8(d), per GPU: E_p (4 + vb) + 4 (N_p + 1) + N vb + N_p vb
+    alg = info.nnz / world * (4 + vb) + 4 * (info.n_nodes / world + 1) + info.n_nodes * vb + info.n_nodes / world * vb
+    peak, _ = measured_peak_gbs()
     return {"workload": f"C4-style: one synthetic Twitter-shaped graph ({info.n_nodes} nodes, {info.nnz} links) row-partitioned x{world}, "
                         f"single seed, 20 iterations; the epilogue kernel stores each rank's slice of x into the peers' copies "
                         f"over NVLink (CUDA IPC), 16-byte ncclAllReduce per iteration",
@@ -335,6 +346,9 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
             "gteps": round(info.nnz * N_ITER * steps / (it_ms * 1e-3) / 1e9, 2), "ms_per_iteration": round(per_iter_ms, 4),
             "rows_rank0": [info.row_begin, info.row_end],
             "allgather_bytes_per_rank_per_iteration": int(gathered),
+            "hbm": {"algorithmic_bytes_per_gpu_per_iteration": int(alg), "achieved": round(alg / (per_iter_ms * 1e-3) / 1e9, 1),
+                    "peak": peak, "unit": "GB/s", "frac": round(alg / (per_iter_ms * 1e-3) / 1e9 / peak, 4)},
+            "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1), "device_bytes": info.device_bytes},
             "nvlink": {"achieved_lower_bound": round(gathered / (per_iter_ms * 1e-3) / 1e9, 1), "peak": 900.0, "unit": "GB/s",
                        "note": "bytes received per rank / whole iteration time (SpMV slice + epilogue with peer stores + allReduce)"},
             "top10_head": top[:3]}
