@@ -63,7 +63,7 @@ typedef struct rwr_opts {
     int32_t relabel;       /* 0 = auto (on): internal relabel by descending out-degree; 1 = off                 */
     int32_t hub_entries;   /* x entries staged in shared memory per CTA; -1 = auto, 0 = none                    */
     int32_t batch_width;   /* seed columns per SpMM tile; 0 = auto                                              */
-    int32_t kernel;        /* SpMV kernel: 0 = warp-streamed edge stream (default); 1 = pipelined producer/consumer; 2 = phased */
+    int32_t kernel;        /* reserved, must be 0 (the warp-streamed edge-stream kernels are the only SpMV path)          */
     uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
     int32_t hot_min_degree;/* nodes with fewer explicit links are clustered by first neighbour; 0 = auto (8), 1 = off */
     int32_t reserved1;

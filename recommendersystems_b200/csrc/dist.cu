@@ -239,7 +239,6 @@ int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opt
         rwr_opts o;
         if (opts) o = *opts; else { memset(&o, 0, sizeof(o)); o.hub_entries = -1; }
         o.device = comm->device;
-        if (o.kernel != 0) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned graphs run the warp-streamed kernel (rwr_opts.kernel = 0) only");
         graph_init_device(g, &o);
         g->comm = comm;
         synth_generate_device(g, spec);
@@ -263,7 +262,6 @@ int rwr_graph_create_partitioned(int32_t n_nodes, const int64_t* node_id, const 
     rwr_opts o;
     if (opts) o = *opts; else { memset(&o, 0, sizeof(o)); o.hub_entries = -1; }
     o.device = comm->device;
-    if (o.kernel != 0) { rwr_set_error("row-partitioned graphs run the warp-streamed kernel (rwr_opts.kernel = 0) only"); return RWR_E_UNSUPPORTED; }
     return rwr_graph_create_flat(n_nodes, node_id, node_type, n_links, src, dst, etype, w, &o, comm, out);
 }
 

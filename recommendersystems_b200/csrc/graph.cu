@@ -292,6 +292,7 @@ void graph_init_device(rwr_graph* g, const rwr_opts* opts) {
         if (g->opts.device >= ndev) RWR_FAIL(RWR_E_INVALID, "device %d out of range (%d devices)", g->opts.device, ndev);
         CUDA_CHECK(cudaSetDevice(g->opts.device));
     }
+    if (g->opts.kernel != 0) RWR_FAIL(RWR_E_INVALID, "rwr_opts.kernel is reserved and must be 0");
     CUDA_CHECK(cudaGetDevice(&g->device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, g->device));

@@ -6,8 +6,6 @@
 struct IterCtl {
     double S;          // restart mass of the iteration being computed: sum_{non-dangling}(r - fl((1-c) r)) + sum_{dangling} r
     double resid;      // last L1 residual sum |r - y|  (Model.cs:110-115)
-    double seed_sum;   // pull sum of the seed row, parked by the SpMV for the fix-up kernel
-    int seed_flag;
     int done;          // threshold mode: converged, later launches are no-ops
     int iters;         // deliverRanks() calls performed
     unsigned ticket;

@@ -26,7 +26,7 @@ C015 = rs.widen_float(0.15)
 
 CASES = ["kat_8c", "small_a", "small_b"]
 OPTS = [dict(), dict(relabel=False), dict(hub_entries=0), dict(relabel=False, hub_entries=0, layout=N.LAYOUT_VALUED),
-        dict(kernel=1), dict(kernel=2), dict(layout=N.LAYOUT_VALUED)]
+        dict(layout=N.LAYOUT_VALUED), dict(hot_min_degree=1), dict(hub_entries=64)]
 
 
 def assert_close_fp64(got, want, what=""):
@@ -346,7 +346,7 @@ def test_medium_graph_hubs_cross_chunks():
                 n_friend=120_000, n_follow=20_000, n_mention=3_000, undefined_per_mille=50, scramble=1, p1_byte=40)
     cpu = O.synth_generate(spec)
     og = oracle_graph(cpu)
-    for opts in (dict(), dict(relabel=False, hub_entries=0), dict(kernel=1), dict(kernel=2)):
+    for opts in (dict(), dict(relabel=False, hub_entries=0), dict(hub_entries=256, hot_min_degree=3)):
         gg = rs.Graph.synthetic(spec, **opts)
         gg.buildGraph()
         info = gg.info()
