@@ -739,6 +739,7 @@ void rwr_graph_destroy(rwr_graph* g) {
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     dist_release_p2p(g);
+    for (auto& ig : g->iter_graph) if (ig.exec) cudaGraphExecDestroy(ig.exec);
     if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
     delete g;
 }

@@ -85,6 +85,14 @@ struct rwr_graph {
     std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
 
 
+    // fixed-count runs replay a captured CUDA graph of their n_iter x (k_spmv_ws, k_cutrows_ws, k_finish_ws) launches: small
+    // graphs (the reference's ego networks are a few thousand nodes) are launch-bound otherwise.  One per precision.
+    struct IterGraph {
+        cudaGraphExec_t exec = nullptr;
+        int n_iter = 0, hub = 0;
+        double c = 0.0;
+        const void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    } iter_graph[2];
     float build_ms = 0.f, synth_ms = 0.f;
     int sm_count = 148;
     int max_smem_optin = 0;

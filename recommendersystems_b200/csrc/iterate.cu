@@ -28,6 +28,7 @@ __global__ void k_init(int n, int seed, T omc, const T* __restrict__ inv, T* __r
     if (j == 0) {
         ctl->resid = 0.0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0;
         ctl->tile_ctr = 0;
+        ctl->seed = seed;
         if (seed < 0) ctl->S = S_uniform;
     }
     if (j >= n) return;
@@ -200,13 +201,46 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     T* x_nxt = xb;
     int launched = 0;
     if (mode == 0) {
-        for (int it = 0; it < n_iter; it++) {
-            p.x = x_cur; p.x_next = x_nxt; p.r_prev = nullptr; p.y = y_out;
-            set_peers<T>(g, p, x_nxt);
-            launch_iteration<T>(g, p, /*resid=*/false, 0.0, 0);
-            std::swap(x_cur, x_nxt);
-            launched++;
+        auto launch_all = [&]() {
+            for (int it = 0; it < n_iter; it++) {
+                p.x = x_cur; p.x_next = x_nxt; p.r_prev = nullptr; p.y = y_out;
+                set_peers<T>(g, p, x_nxt);
+                launch_iteration<T>(g, p, /*resid=*/false, 0.0, 0);
+                std::swap(x_cur, x_nxt);
+            }
+        };
+        static const bool no_graph = getenv("RWR_NO_GRAPH") != nullptr;
+        if (n_iter >= 2 && dist_n_ranks(g->comm) == 1 && !no_graph) {
+            // replay (or capture once) the graph of the whole loop; nothing in it depends on the seed
+            rwr_graph::IterGraph& ig = g->iter_graph[Prec<T>::id];
+            const void* key[8] = {xa, xb, y_out, ws.ctl.p, ws.head.p, ws.carry.p, ws.slot_S.p, ws.slot_R.p};
+            const bool hit = ig.exec && ig.n_iter == n_iter && ig.hub == hub && ig.c == c && memcmp(ig.ptr, key, sizeof(key)) == 0;
+            if (!hit) {
+                if (ig.exec) { cudaGraphExecDestroy(ig.exec); ig.exec = nullptr; }
+                const int64_t counted = g->pool.launches;
+                cudaGraph_t graph = nullptr;
+                CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+                try {
+                    launch_all();
+                } catch (...) {
+                    cudaStreamEndCapture(st, &graph);
+                    if (graph) cudaGraphDestroy(graph);
+                    throw;
+                }
+                CUDA_CHECK(cudaStreamEndCapture(st, &graph));
+                const cudaError_t err = cudaGraphInstantiate(&ig.exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (err != cudaSuccess) { ig.exec = nullptr; CUDA_CHECK(err); }
+                g->pool.launches = counted;
+                ig.n_iter = n_iter; ig.hub = hub; ig.c = c;
+                memcpy(ig.ptr, key, sizeof(key));
+            }
+            CUDA_CHECK(cudaGraphLaunch(ig.exec, st));
+            g->pool.launches += 3 * (int64_t)n_iter;
+        } else {
+            launch_all();
         }
+        launched = n_iter;
         *iters_out = n_iter;
         *resid_out = NAN;
     } else {

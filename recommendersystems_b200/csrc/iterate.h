@@ -9,6 +9,8 @@ struct IterCtl {
     int done;          // threshold mode: converged, later launches are no-ops
     int iters;         // deliverRanks() calls performed
     unsigned ticket;
+    int seed;           // internal label of the seed, -1: uniform restart.  Read by k_finish_ws from here, not from its
+                        // launch parameters, so that a captured iteration graph can be replayed for any seed
     unsigned tile_ctr;  // k_spmv_ws: next tile to hand out (reset by k_finish_ws)
     double red[2];     // row-partitioned graphs: this rank's {restart mass, residual} partials, summed over the ranks in place
 };

@@ -475,14 +475,15 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
     IterCtl* ctl = p.ctl;
     if (ctl->done) return;
     const double S = ctl->S;
-    const T uni_add = (T)((p.seed < 0) ? S * p.inv_n : 0.0);
+    const int seed = ctl->seed;
+    const T uni_add = (T)((seed < 0) ? S * p.inv_n : 0.0);
     const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
     double accS = 0.0, accR = 0.0;
     for (int row = p.row_begin + blockIdx.x * FIN_THREADS + threadIdx.x; row < p.row_end; row += gridDim.x * FIN_THREADS) {
         T y = ld_stream(p.y + row, pol_first);
         const T invr = ld_stream(p.inv + row, pol_first);
-        if (row == p.seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
-        if (p.seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
+        if (row == seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
+        if (seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
         const T rw = mul_rn(p.omc, y);
         // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
         const T xn = mul_rn(rw, invr);
