@@ -294,13 +294,18 @@ void graph_init_device(rwr_graph* g, const rwr_opts* opts) {
     }
     if (g->opts.kernel != 0) RWR_FAIL(RWR_E_INVALID, "rwr_opts.kernel is reserved and must be 0");
     CUDA_CHECK(cudaGetDevice(&g->device));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, g->device));
-    if (prop.major < 10)
-        RWR_FAIL(RWR_E_CUDA, "device %d is sm_%d%d; librwr_b200 is built for sm_100a only", g->device, prop.major, prop.minor);
+    // three attribute queries instead of cudaGetDeviceProperties (about a millisecond per call, and the reference
+    // creates one graph per ego network)
+    int major = 0, minor = 0, sms = 0, smem_optin = 0;
+    CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, g->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, g->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g->device));
+    CUDA_CHECK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, g->device));
+    if (major < 10)
+        RWR_FAIL(RWR_E_CUDA, "device %d is sm_%d%d; librwr_b200 is built for sm_100a only", g->device, major, minor);
     g->scratch.pool = &g->pool;
-    g->sm_count = prop.multiProcessorCount;
-    g->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    g->sm_count = sms;
+    g->max_smem_optin = smem_optin;
     if (g->opts.stream) {
         g->stream = (cudaStream_t)(uintptr_t)g->opts.stream;
         g->own_stream = false;
