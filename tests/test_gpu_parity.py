@@ -543,3 +543,45 @@ def test_experiment_style_holdout_evaluation():
         h1, ap1 = rs.evaluate(full_rank, test[int(u)])
         h2, ap2 = O.evaluate(a, test[int(u)])
         assert h1 == h2 == len(test[int(u)]) and abs(ap1 - ap2) <= 1e-12
+
+
+# ------------------------------------------------------------------------------------------ concurrency (Program.cs:11, :61-66)
+def test_concurrent_handles_from_several_threads():
+    """The reference runs up to 10 ego networks at once, each thread on its own Graph / Recommender.  Every handle owns
+    its stream, pools and cached iteration graph: concurrent create / build / recommend / destroy must not interfere."""
+    import threading
+    n_threads, rounds = 6, 3
+    specs = [dict(seed=500 + t, n_users=300 + 40 * t, n_items=2500 + 300 * t, n_third=30, authorship_per_mille=800,
+                  n_like=9000 + 1000 * t, n_friend=2000, n_follow=100, n_mention=0 if t % 2 else 200, undefined_per_mille=20,
+                  scramble=1, p1_byte=61) for t in range(n_threads)]
+    want = []
+    for sp in specs:
+        links = O.synth_generate(sp)
+        og = oracle_graph(links)
+        deg = np.bincount(links["src"], minlength=og.n)
+        seeds = [int(s) for s in np.flatnonzero(deg[:sp["n_users"]] > 0)[:4]]
+        want.append((links, seeds, [og.recommend(s, 0.15, 9, top_n=8)[0].tolist() for s in seeds]))
+    errors = []
+
+    def worker(t):
+        try:
+            links, seeds, lists = want[t]
+            for _ in range(rounds):
+                g = gpu_graph(links)
+                rec = rs.Recommender(g)
+                for s, w in zip(seeds, lists):
+                    got = [p[0] for p in rec.Recommendation(s, 0.15, 9, 8)]
+                    assert got == w, (t, s)
+                ids, sc, cnt = rec.RecommendationBatch(seeds, 0.15, 9, 8)
+                for i, w in enumerate(lists):
+                    assert ids[i, :cnt[i]].tolist() == w, (t, i)
+                g.close()
+        except Exception as e:      # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
