@@ -206,12 +206,15 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     # ---- C3 leg: batched seeds through the SpMM tiles (8 FP64 / 16 FP32 columns per matrix pass), seeds sharded
     #      over the ranks with no communication; host seed list in, top-10 lists out
-    nb = args.batch_seeds
-    bseeds = pick_seeds(raw_deg, spec["n_users"], nb, offset=100_000 + rank * nb)
+    # C3 as specified: ONE list of --batch-seeds (1,024) seed users, rank j takes the block [j*S/P, (j+1)*S/P)
+    from recommendersystems_b200.sharding import shard_seeds
+    all_bseeds = pick_seeds(raw_deg, spec["n_users"], args.batch_seeds, offset=100_000)
+    bseeds = shard_seeds(all_bseeds, rank, world)
+    nb = len(bseeds)
     batched = {}
     for bprec, bname in ((rs.FP64, "fp64"), (rs.FP32, "fp32")):
         brec = rs.Recommender(g, bprec)
-        brec.RecommendationBatch(bseeds[:16], C_FLOAT, N_ITER, TOP_K)
+        brec.RecommendationBatch(all_bseeds[:16], C_FLOAT, N_ITER, TOP_K)
         barrier()
         t0 = time.perf_counter()
         brec.RecommendationBatch(bseeds, C_FLOAT, N_ITER, TOP_K)
@@ -283,14 +286,16 @@ def run_ours(args):
                     "d2h_bytes_per_step": TOP_K * 16 + 4, "ms_per_step": round(e2e_ms / args.steps, 4),
                     "seeds_per_s": round(args.steps * world / (e2e_ms * 1e-3), 2),
                     "api": "Recommender.Recommendation(seed, 0.15f, 20, 10) -> rwr_recommend (C ABI)"},
-            "batched": {"workload": f"C3: {nb} seeds per GPU as SpMM tiles on the same graph, top-10 per seed, seeds "
-                                    f"sharded x{world} (no collective)",
-                        "fp64": {"seeds_per_s": round(nb * world / b64_s, 1),
-                                 "seed_gteps_e2e": round(nnz * N_ITER * nb * world / b64_s / 1e9, 1),
-                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * nb * world / b64_it / 1e9, 1)},
-                        "fp32": {"seeds_per_s": round(nb * world / b32_s, 1),
-                                 "seed_gteps_e2e": round(nnz * N_ITER * nb * world / b32_s / 1e9, 1),
-                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * nb * world / b32_it / 1e9, 1)}},
+            "batched": {"workload": f"C3: {args.batch_seeds} seed users as SpMM tiles (8 FP64 / 16 FP32 columns) on the same graph, "
+                                    f"top-10 per seed, the seed list sharded x{world} in contiguous blocks (no collective); "
+                                    f"host seed list in, top-10 lists out",
+                        "seeds_total": args.batch_seeds,
+                        "fp64": {"seeds_per_s": round(args.batch_seeds / b64_s, 1),
+                                 "seed_gteps_e2e": round(nnz * N_ITER * args.batch_seeds / b64_s / 1e9, 1),
+                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * args.batch_seeds / b64_it / 1e9, 1)},
+                        "fp32": {"seeds_per_s": round(args.batch_seeds / b32_s, 1),
+                                 "seed_gteps_e2e": round(nnz * N_ITER * args.batch_seeds / b32_s / 1e9, 1),
+                                 "seed_gteps_iteration_loop": round(nnz * N_ITER * args.batch_seeds / b32_it / 1e9, 1)}},
             "row_partitioned": parted,
             "gpu_launches": int(launches),
             "clocks": clocks,
@@ -367,10 +372,44 @@ def cpu_baseline_leg(g, seed: int, nnz: int, sample_iters: int):
     og.run(seed, O.widen_float(C_FLOAT), n_iter=sample_iters)
     dt = time.perf_counter() - t0
     og.close()
-    return {"value": round(nnz * sample_iters / dt / 1e9, 4), "unit": "GTEPS", "cores": 1, "kind": "port",
+    c1 = c1_literal_leg()
+    return {"value": round(nnz * sample_iters / dt / 1e9, 4), "unit": "GTEPS", "cores": 1, "kind": "port", "c1_literal": c1,
             "sample": f"{sample_iters} of 20 iterations of one seed on the full graph, collapsed O(E+N) form "
                       f"(the literal O(N^2) restart loops of Model.cs:92-93 are infeasible beyond ~10k nodes), {dt:.1f} s",
             "host_cores": os.cpu_count()}
+
+
+def c1_literal_leg():
+    """BASELINE configs[0]: the reference's CPU path AS WRITTEN (the O(N^2) restart loops of Model.cs:92-93, :96-97) on a
+    C1-sized ego network, one core, against the same request on the GPU."""
+    import numpy as np
+    import oracle as O
+    import recommendersystems_b200 as rs
+    spec = dict(seed=20260101, n_users=1000, n_items=9000, n_third=200, authorship_per_mille=800, n_like=36000,
+                n_friend=8000, n_follow=600, n_mention=400, undefined_per_mille=100, scramble=1, p1_byte=61, reserved=0)
+    links = O.synth_generate(spec)
+    og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+    assert og.build() == 0
+    seed = int(np.flatnonzero(np.bincount(links["src"], minlength=og.n)[:1000] > 0)[0])
+    iters = 5
+    t0 = time.perf_counter()
+    og.run(seed, O.widen_float(C_FLOAT), n_iter=iters, literal=True)
+    cpu_s = (time.perf_counter() - t0) * N_ITER / iters
+    nnz_c1 = og.nnz()
+    og.close()
+    g = rs.Graph.from_arrays(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+    g.buildGraph()
+    rec = rs.Recommender(g)
+    for _ in range(5):
+        rec.Recommendation(seed, C_FLOAT, N_ITER, TOP_K)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        rec.Recommendation(seed, C_FLOAT, N_ITER, TOP_K)
+    gpu_s = (time.perf_counter() - t0) / 20
+    g.close()
+    return {"workload": f"C1: ego network of {len(links['node_id'])} nodes / {nnz_c1} links, Model.run(20), literal O(N^2) loops, 1 core",
+            "cpu_seconds_per_request": round(cpu_s, 3), "sample": f"{iters} of 20 iterations, scaled",
+            "gpu_seconds_per_request": round(gpu_s, 6), "gpu_api": "Recommender.Recommendation(seed, 0.15f, 20, 10)"}
 
 
 # ======================================================================================================= reference arm
@@ -435,7 +474,7 @@ def main():
     ap.add_argument("--scale", type=float, default=float(os.environ.get("RWR_BENCH_SCALE", "1.0")))
     ap.add_argument("--cpu-iters", type=int, default=2, help="iterations of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--batch-seeds", type=int, default=64, help="seeds per GPU of the batched (C3) leg")
+    ap.add_argument("--batch-seeds", type=int, default=1024, help="seeds of the batched (C3) leg, all ranks together")
     ap.add_argument("--no-partitioned", action="store_true", help="skip the row-partitioned leg (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)

@@ -66,7 +66,10 @@ typedef struct rwr_opts {
     int32_t kernel;        /* reserved, must be 0 (the warp-streamed edge-stream kernels are the only SpMV path)          */
     uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
     int32_t hot_min_degree;/* nodes with fewer explicit links are clustered by first neighbour; 0 = auto (8), 1 = off */
-    int32_t reserved1;
+    int32_t undefined_type_mask; /* bit t set: links of EdgeType t count as UNDEFINED at buildGraph() -- they stay in  */
+                           /* `edges` but leave the matrix, as the methodology switches of Experiment.cs:84-101 do   */
+                           /* by retyping FRIENDSHIP links (mask 1 << RWR_EDGE_FRIENDSHIP); LIKE links masked here   */
+                           /* still exclude their targets from the recommendation (Recommender.cs:20-24)             */
 } rwr_opts;
 
 /* Deterministic synthetic generator (this repository's spec; replaces TweetRecommender/DataLoader.cs:256-436

@@ -20,7 +20,7 @@ LAYOUT_AUTO, LAYOUT_VALUED, LAYOUT_INDEX = 0, 1, 2
 class rwr_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("relabel", C.c_int32), ("hub_entries", C.c_int32),
                 ("batch_width", C.c_int32), ("kernel", C.c_int32), ("stream", C.c_uint64),
-                ("hot_min_degree", C.c_int32), ("reserved1", C.c_int32)]
+                ("hot_min_degree", C.c_int32), ("undefined_type_mask", C.c_int32)]
 
 
 class rwr_synth_spec(C.Structure):

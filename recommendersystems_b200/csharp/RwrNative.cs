@@ -15,7 +15,7 @@ namespace Recommenders.RWRBased.Native {
     public struct RwrOpts {
         public int device, layout, relabel, hub_entries, batch_width, kernel;
         public ulong stream;
-        public int hot_min_degree, reserved1;
+        public int hot_min_degree, undefined_type_mask;
         public static RwrOpts Default() { return new RwrOpts { device = -1, hub_entries = -1 }; }
     }
 

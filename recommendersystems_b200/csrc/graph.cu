@@ -58,11 +58,15 @@ __global__ void k_lower_bounds(const KeyT* __restrict__ keys, size_t e, int32_t 
 }
 
 // K1: flag explicit links (type != UNDEFINED) and validate their targets (IndexOutOfRange at Model.cs:87)
+// `mask`: bit t set = links of EdgeType t count as UNDEFINED (the methodology switches of Experiment.cs:84-101, which
+// retype FRIENDSHIP links to UNDEFINED before buildGraph(), as one option instead of a rewrite of the link list)
+__device__ __forceinline__ bool link_is_explicit(u8 t, u32 mask) { return t != RWR_EDGE_UNDEFINED && !((mask >> (t & 31)) & 1u); }
+
 __global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __restrict__ dst, size_t e0, int32_t n,
-                                 u32* __restrict__ flags, int* bad) {
+                                 u32 mask, u32* __restrict__ flags, int* bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e0) {
-        u32 f = type[i] != RWR_EDGE_UNDEFINED;
+        u32 f = link_is_explicit(type[i], mask);
         if (f) {
             int32_t d = dst[i];
             if (d < 0 || d >= n) *bad = 1;
@@ -73,10 +77,10 @@ __global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __r
 
 // K3: stable compaction of the explicit links (insertion order kept: pos is an exclusive scan of the flags)
 __global__ void k_compact(const u8* __restrict__ type, const u32* __restrict__ pos, const int32_t* __restrict__ src,
-                          const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0,
+                          const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0, u32 mask,
                           int32_t* __restrict__ src_of, int32_t* __restrict__ col, double* __restrict__ wv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < e0 && type[i] != RWR_EDGE_UNDEFINED) {
+    if (i < e0 && link_is_explicit(type[i], mask)) {
         u32 p = pos[i];
         src_of[p] = src[i];
         col[p] = dst[i];
@@ -382,7 +386,7 @@ static void graph_build_impl(rwr_graph* g) {
     pos.alloc(e0);
     total.alloc(1);
     if (e0) {
-        k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, n, pos.p, bad.p);
+        k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, n, (u32)g->opts.undefined_type_mask, pos.p, bad.p);
         KERNEL_CHECK();
     }
     prim::exclusive_scan<u32>(pos.p, pos.p, e0, total.p, st, &g->pool);
@@ -411,7 +415,7 @@ static void graph_build_impl(rwr_graph* g) {
         g->src_of_own.alloc(nnz, &g->pool);
         wv_own.alloc(nnz);
         k_compact<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, g->raw_src.p, g->raw_dst.p, g->raw_w.p, e0,
-                                                g->src_of_own.p, g->col_own.p, wv_own.p);
+                                                (u32)g->opts.undefined_type_mask, g->src_of_own.p, g->col_own.p, wv_own.p);
         k_row_ptr_from_pos<<<grid_for((size_t)n + 1), 256, 0, st>>>(g->raw_ptr.p, pos.p, e0, (u32)nnz, n, g->row_ptr_own.p);
         KERNEL_CHECK();
         g->row_ptr = g->row_ptr_own.p;

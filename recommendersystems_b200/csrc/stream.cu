@@ -548,7 +548,10 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     const size_t smem = (size_t)WS_HDR + (size_t)p.hub * sizeof(T);
     auto kern = valued ? k_spmv_ws<T, true> : k_spmv_ws<T, false>;
     const int threads = (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS) * 32;
-    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the opt-in ceiling is a per-function, per-device setting shared by every handle and thread: always the device
+    // maximum (a per-launch value would race between threads whose graphs have different hub sizes); the carve-out a
+    // launch gets still follows the dynamic size it asks for
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem_optin));
     kern<<<ws_main_grid(g), threads, smem, g->stream>>>(p);
     KERNEL_CHECK();
 }

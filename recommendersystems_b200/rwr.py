@@ -99,10 +99,13 @@ class SynthSpec(dict):
 
 
 def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_width=0, stream=0, kernel=0,
-          hot_min_degree=0) -> N.rwr_opts:
+          hot_min_degree=0, undefined_types=()) -> N.rwr_opts:
+    mask = 0
+    for t in undefined_types:            # EdgeType values that count as UNDEFINED at buildGraph() (Experiment.cs:84-101)
+        mask |= 1 << int(t)
     return N.rwr_opts(device=int(device), layout=int(layout), relabel=0 if relabel else 1, hub_entries=int(hub_entries),
                       batch_width=int(batch_width), kernel=int(kernel), stream=int(stream),
-                      hot_min_degree=int(hot_min_degree), reserved1=0)
+                      hot_min_degree=int(hot_min_degree), undefined_type_mask=mask)
 
 
 class Comm:

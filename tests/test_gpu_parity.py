@@ -585,3 +585,33 @@ def test_concurrent_handles_from_several_threads():
     for th in threads:
         th.join()
     assert not errors, errors
+
+
+# ------------------------------------------------------------------------------------------ methodology switch (Experiment.cs:84-101)
+def test_undefined_type_mask_equals_retyping_the_links():
+    """`undefined_types=[FRIENDSHIP]` must give the graph the reference builds after rewriting every FRIENDSHIP link to
+    UNDEFINED (Experiment.cs:84-101): same CSR, same ranks, same recommendation; raw links stay exportable."""
+    g = load_golden("small_b")
+    inp = {k: np.asarray(v) for k, v in g["input"].items()}
+    et = inp["etype"].astype(np.int32)
+    assert (et == rs.EdgeType.FRIENDSHIP).any()
+    retyped = dict(inp)
+    retyped["etype"] = np.where(et == rs.EdgeType.FRIENDSHIP, rs.EdgeType.UNDEFINED, et).astype(np.int32)
+    og = oracle_graph(retyped)
+    gm = gpu_graph(inp, undefined_types=[rs.EdgeType.FRIENDSHIP])
+    rp, col, val = gm.csr()
+    orp, ocol, oval = og.csr()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(bits(val), bits(oval))
+    assert np.array_equal(gm.export_links()["etype"], et)                    # the edge list itself is untouched
+    deg = gm.degrees()
+    seed = int(np.flatnonzero(deg > 0)[0])
+    want, _ = og.run(seed, C015, n_iter=12)
+    r = run_fixed(gm, [seed], C015, 12)
+    assert_close_fp64(r.scores(0), want, "masked FRIENDSHIP")
+    r.close()
+    try:
+        ids, sc = og.recommend(seed, 0.15, 12, top_n=10)
+    except KeyError:
+        return
+    top = rs.Recommender(gm).Recommendation(seed, 0.15, 12, 10)
+    same_ranking([p[0] for p in top], [p[1] for p in top], ids, sc)
