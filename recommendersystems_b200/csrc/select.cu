@@ -197,6 +197,133 @@ __global__ void k_mark_excluded(const int32_t* __restrict__ raw_dst, const u8* _
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ top-k of a whole seed tile
+// The batched path keeps the ranks of B seeds row-major, Y[n, B].  Scanning one column at a time reads every 32-byte
+// sector of Y once per column and pass; these kernels handle all B columns of a row at once (coalesced), with the same
+// exact scheme as k_topk_bound / k_topk_scan: per-column lower bound from block maxima, then only the candidates at or
+// above the bound are kept -- here appended to a per-column list (they are few) that k_topk_merge reduces.
+constexpr int TILE_MAXB = 16;
+constexpr int TILE_CAND_CAP = 1 << 16;          // candidates kept per column; more (e.g. everything ties at 0) -> per-column path
+
+__global__ void k_mark_excluded_tile(const int32_t* __restrict__ raw_dst, const u8* __restrict__ raw_type,
+                                     const u32* __restrict__ raw_ptr, const int32_t* __restrict__ seeds /* original labels */,
+                                     const int32_t* __restrict__ new_of_old, int n, size_t words, u32* __restrict__ excl,
+                                     int* __restrict__ no_links) {
+    const int col = blockIdx.y;
+    const int seed = seeds[col];
+    const u32 b = raw_ptr[seed], e = raw_ptr[seed + 1];
+    if (b == e && blockIdx.x == 0 && threadIdx.x == 0) no_links[col] = 1;      // KeyNotFoundException, Recommender.cs:21
+    u32* ex = excl + (size_t)col * words;
+    for (u32 i = b + blockIdx.x * blockDim.x + threadIdx.x; i < e; i += gridDim.x * blockDim.x) {
+        if (raw_type[i] == RWR_EDGE_LIKE) {
+            const int32_t d = raw_dst[i];
+            if (d >= 0 && d < n) {
+                const int j = new_of_old[d];
+                atomicOr(&ex[j >> 5], 1u << (j & 31));
+            }
+        }
+    }
+}
+
+template <typename T, int B>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_bound_tile(const T* __restrict__ y, const u8* __restrict__ type_int,
+                                                                  const u32* __restrict__ excl, size_t words, int n, int cols,
+                                                                  u64* __restrict__ block_max /* [grid][B] */) {
+    __shared__ u64 sm[TOPK_THREADS];
+    const int col = threadIdx.x % B, rlane = threadIdx.x / B;
+    constexpr int RPB = TOPK_THREADS / B;                    // rows per block step
+    u64 best = 0;
+    if (col < cols) {
+        const u32* ex = excl + (size_t)col * words;
+        for (int j = blockIdx.x * RPB + rlane; j < n; j += gridDim.x * RPB) {
+            if (type_int[j] != RWR_NODE_ITEM) continue;
+            const u64 key = score_key((double)y[(size_t)j * B + col]);
+            if (key <= best) continue;
+            if ((ex[j >> 5] >> (j & 31)) & 1u) continue;
+            best = key;
+        }
+    }
+    sm[threadIdx.x] = best;
+    __syncthreads();
+    if (threadIdx.x < B) {
+        u64 m = 0;
+        for (int i = threadIdx.x; i < TOPK_THREADS; i += B) m = sm[i] > m ? sm[i] : m;
+        block_max[(size_t)blockIdx.x * B + threadIdx.x] = m;
+    }
+}
+
+// k-th largest block maximum of every column (rank counting, ties by index); 0 when there are fewer than k blocks
+template <int B>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_bounds_tile(const u64* __restrict__ block_max, int nb, int k,
+                                                                   u64* __restrict__ bound /* [B] */) {
+    __shared__ u64 sm[TOPK_MAX_GRID];
+    const int col = blockIdx.x;
+    for (int i = threadIdx.x; i < nb; i += TOPK_THREADS) sm[i] = block_max[(size_t)i * B + col];
+    if (threadIdx.x == 0) bound[col] = 0;
+    __syncthreads();
+    if (nb < k) return;
+    for (int i = threadIdx.x; i < nb; i += TOPK_THREADS) {
+        const u64 v = sm[i];
+        int rank = 0;
+        for (int j = 0; j < nb; j++) rank += (sm[j] > v) || (sm[j] == v && j < i);
+        if (rank == k - 1) bound[col] = v;
+    }
+}
+
+template <typename T, int B>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_scan_tile(const T* __restrict__ y, const u8* __restrict__ type_int,
+                                                                 const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
+                                                                 size_t words, int n, int cols, const u64* __restrict__ bound,
+                                                                 Cand* __restrict__ cand /* [B][CAP] */, int* __restrict__ cnt) {
+    const int col = threadIdx.x % B, rlane = threadIdx.x / B;
+    constexpr int RPB = TOPK_THREADS / B;
+    if (col >= cols) return;
+    const u64 bd = bound[col];
+    const u32* ex = excl + (size_t)col * words;
+    for (int j = blockIdx.x * RPB + rlane; j < n; j += gridDim.x * RPB) {
+        if (type_int[j] != RWR_NODE_ITEM) continue;
+        const u64 key = score_key((double)y[(size_t)j * B + col]);
+        if (key < bd) continue;
+        if ((ex[j >> 5] >> (j & 31)) & 1u) continue;
+        const int slot = atomicAdd(&cnt[col], 1);
+        if (slot < TILE_CAND_CAP) {
+            Cand c;
+            c.key = key; c.id = id_int[j]; c.idx = j;
+            cand[(size_t)col * TILE_CAND_CAP + slot] = c;
+        }
+    }
+}
+
+// one block per column: the k best of the column's candidate list
+template <typename T>
+__global__ void __launch_bounds__(TOPK_THREADS) k_topk_merge_tile(const Cand* __restrict__ cand, const int* __restrict__ cnt, int k,
+                                                                  const T* __restrict__ y, int ld, int64_t* __restrict__ out_ids,
+                                                                  double* __restrict__ out_scores, int* __restrict__ out_count) {
+    __shared__ Cand sm_best[TOPK_THREADS / 32];
+    __shared__ int sm_owner[TOPK_THREADS / 32 + 1];
+    __shared__ Cand result[TOPK_MAX];
+    const int col = blockIdx.x;
+    const int n_cands = min(cnt[col], TILE_CAND_CAP);
+    const Cand* cands = cand + (size_t)col * TILE_CAND_CAP;
+    Cand list[TOPK_MAX];
+#pragma unroll
+    for (int i = 0; i < TOPK_MAX; i++) { list[i].key = 0; list[i].id = 0; list[i].idx = -1; }
+    for (int j = threadIdx.x; j < n_cands; j += TOPK_THREADS) list_insert(list, cands[j]);
+    block_extract(list, k, result, sm_best, sm_owner);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int c = 0;
+        for (int i = 0; i < k; i++) {
+            if (result[i].idx < 0) break;
+            out_ids[(size_t)col * k + i] = result[i].id;
+            out_scores[(size_t)col * k + i] = (double)y[(size_t)result[i].idx * ld + col];
+            c++;
+        }
+        out_count[col] = c;
+    }
+}
+
 __global__ void k_lookup(const int32_t* __restrict__ table, const int32_t* __restrict__ keys, int n, int32_t* __restrict__ out) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = table[keys[i]];
@@ -469,11 +596,13 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
     if (sizeof(T) == 4) ensure_fp32_arrays(g);
     // internal labels of all seeds in one go
     std::vector<int32_t> n2o((size_t)n_seeds);
+    Scratch<int32_t> d_seeds_all;                  // original labels of all seeds (the tile top-k reads their raw link ranges)
+    d_seeds_all.alloc(&g->scratch, n_seeds);
     {
-        Scratch<int32_t> d_seeds, d_int;
-        d_seeds.alloc(&g->scratch, n_seeds); d_int.alloc(&g->scratch, n_seeds);
-        CUDA_CHECK(cudaMemcpyAsync(d_seeds.p, seeds, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, st));
-        k_lookup<<<div_up((size_t)n_seeds, 256), 256, 0, st>>>(g->new_of_old.p, d_seeds.p, n_seeds, d_int.p);
+        Scratch<int32_t> d_int;
+        d_int.alloc(&g->scratch, n_seeds);
+        CUDA_CHECK(cudaMemcpyAsync(d_seeds_all.p, seeds, (size_t)n_seeds * 4, cudaMemcpyHostToDevice, st));
+        k_lookup<<<div_up((size_t)n_seeds, 256), 256, 0, st>>>(g->new_of_old.p, d_seeds_all.p, n_seeds, d_int.p);
         KERNEL_CHECK();
         CUDA_CHECK(cudaMemcpyAsync(n2o.data(), d_int.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaStreamSynchronize(st));
@@ -491,6 +620,12 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
     d_ids.alloc(&g->scratch, (size_t)n_seeds * k); d_sc.alloc(&g->scratch, (size_t)n_seeds * k); d_cnt.alloc(&g->scratch, n_seeds);
     CUDA_CHECK(cudaMemsetAsync(d_ids.p, 0, (size_t)n_seeds * k * 8, st));
     CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)n_seeds * k * 8, st));
+    Scratch<u32> excl_t;                           // [B][words] exclusion bitmaps of a tile
+    Scratch<u64> tile_max, tile_bound;             // [grid][B] block maxima, [B] bounds
+    Scratch<Cand> tile_cand;                       // [B][TILE_CAND_CAP]
+    Scratch<int> tile_cnt;                         // [TILE_MAXB] candidate counts | [TILE_MAXB] seeds without links
+    excl_t.alloc(&g->scratch, (size_t)B * words); tile_max.alloc(&g->scratch, (size_t)grid * B); tile_bound.alloc(&g->scratch, TILE_MAXB);
+    tile_cand.alloc(&g->scratch, (size_t)B * TILE_CAND_CAP); tile_cnt.alloc(&g->scratch, 2 * TILE_MAXB);
     cudaEvent_t e0, e1, e2;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
     int64_t launches = 0;
@@ -500,13 +635,39 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
         CUDA_CHECK(cudaEventRecord(e0, st));
         spmm_run_tile<T>(g, n2o.data() + s0, cnt, c, n_iter, y.p, &launches);
         CUDA_CHECK(cudaEventRecord(e1, st));
-        for (int j = 0; j < cnt; j++) {
-            topk_one<T>(g, y.p + j, B, seeds[s0 + j], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)(s0 + j) * k,
-                        d_sc.p + (size_t)(s0 + j) * k, d_cnt.p + s0 + j);
-            launches += 3;
+        // top-k of the whole tile in one pass over Y per step (bound, scan), then one merge block per column
+        CUDA_CHECK(cudaMemsetAsync(excl_t.p, 0, (size_t)B * words * sizeof(u32), st));
+        CUDA_CHECK(cudaMemsetAsync(tile_cnt.p, 0, 2 * TILE_MAXB * sizeof(int), st));
+        k_mark_excluded_tile<<<dim3(8, cnt), 256, 0, st>>>(g->raw_dst.p, g->raw_type.p, g->raw_ptr.p, d_seeds_all.p + s0,
+                                                          g->new_of_old.p, g->n, words, excl_t.p, tile_cnt.p + TILE_MAXB);
+        if (B == 8) {
+            k_topk_bound_tile<T, 8><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, excl_t.p, words, g->n, cnt, tile_max.p);
+            k_topk_bounds_tile<8><<<cnt, TOPK_THREADS, 0, st>>>(tile_max.p, grid, k, tile_bound.p);
+            k_topk_scan_tile<T, 8><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
+                                                                 tile_bound.p, tile_cand.p, tile_cnt.p);
+        } else {
+            k_topk_bound_tile<T, 16><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, excl_t.p, words, g->n, cnt, tile_max.p);
+            k_topk_bounds_tile<16><<<cnt, TOPK_THREADS, 0, st>>>(tile_max.p, grid, k, tile_bound.p);
+            k_topk_scan_tile<T, 16><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
+                                                                  tile_bound.p, tile_cand.p, tile_cnt.p);
         }
+        k_topk_merge_tile<T><<<cnt, TOPK_THREADS, 0, st>>>(tile_cand.p, tile_cnt.p, k, y.p, B, d_ids.p + (size_t)s0 * k,
+                                                          d_sc.p + (size_t)s0 * k, d_cnt.p + s0);
+        KERNEL_CHECK();
+        launches += 5;
+        int h_cnt[2 * TILE_MAXB];
+        CUDA_CHECK(cudaMemcpyAsync(h_cnt, tile_cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaEventRecord(e2, st));
         CUDA_CHECK(cudaEventSynchronize(e2));
+        for (int j = 0; j < cnt; j++) {
+            if (h_cnt[TILE_MAXB + j])
+                RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seeds[s0 + j]);
+            if (h_cnt[j] > TILE_CAND_CAP) {              // too many candidates at the bound (ties): exact per-column path
+                topk_one<T>(g, y.p + j, B, seeds[s0 + j], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)(s0 + j) * k,
+                            d_sc.p + (size_t)(s0 + j) * k, d_cnt.p + s0 + j);
+                launches += 4;
+            }
+        }
         float a = 0.f, b = 0.f;
         CUDA_CHECK(cudaEventElapsedTime(&a, e0, e1));
         CUDA_CHECK(cudaEventElapsedTime(&b, e0, e2));

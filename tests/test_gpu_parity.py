@@ -615,3 +615,27 @@ def test_undefined_type_mask_equals_retyping_the_links():
         return
     top = rs.Recommender(gm).Recommendation(seed, 0.15, 12, 10)
     same_ranking([p[0] for p in top], [p[1] for p in top], ids, sc)
+
+
+def test_batched_topk_with_mass_ties_at_zero():
+    """One iteration from a seed with few neighbours: fewer than k items have a score, the rest tie at exactly 0 and are
+    ordered by id descending (Recommender.cs:34-38).  More than 65,536 such ties per column overflow the tile top-k's
+    candidate list and must fall back to the exact per-column path."""
+    spec = dict(seed=31, n_users=2_000, n_items=120_000, n_third=0, authorship_per_mille=300, n_like=60_000, n_friend=4_000,
+                n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1, p1_byte=100)
+    cpu = O.synth_generate(spec)
+    og = oracle_graph(cpu)
+    gg = rs.Graph.synthetic(spec)
+    gg.buildGraph()
+    like_deg = np.bincount(cpu["src"][cpu["etype"] == 1], minlength=og.n)
+    deg = np.bincount(cpu["src"], minlength=og.n)
+    seeds = [int(u) for u in np.flatnonzero((deg[:2000] > 0) & (like_deg[:2000] <= 3))[:9]]
+    assert len(seeds) == 9
+    rec = rs.Recommender(gg)
+    for n_iter in (1, 2):
+        ids, sc, cnt = rec.RecommendationBatch(seeds, 0.15, n_iter, 10)
+        for i, s in enumerate(seeds):
+            oids, osc = og.recommend(s, 0.15, n_iter, top_n=10)
+            assert cnt[i] == len(oids) == 10
+            same_ranking(ids[i, :cnt[i]], sc[i, :cnt[i]], oids, osc)
+    assert (sc[:, -1] == 0).any()          # the case under test did occur: a list padded with zero-score items
