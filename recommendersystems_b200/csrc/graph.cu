@@ -223,16 +223,29 @@ __global__ void k_assign_cold(const u32* __restrict__ sorted_ids, u32 n_cold, u3
     }
 }
 
-// Row-partitioned graphs: deal the label order (hot nodes by descending degree, then the clustered cold nodes) round-robin
-// to the P slices: position i goes to slice i mod P, at offset i / P.  Slice r holds q + (r < rem) labels (q = n / P,
-// rem = n mod P), so labels stay dense in [0, n).  Every contiguous slice then holds every P-th node of that order:
-// equal rows AND (statistically) equal link counts per rank, and the hottest nodes still come first in a slice.
-__global__ void k_interleave_labels(const int32_t* __restrict__ old_of_new_in, int32_t n, int32_t parts,
-                                    int32_t* __restrict__ old_of_new, int32_t* __restrict__ new_of_old) {
+// Row-partitioned graphs: deal the label order over the P slices so that every contiguous slice of labels holds
+// near-equal rows AND near-equal link counts.  The hot part of the order (degree-sorted) is dealt node by node --
+// position i to slice i mod P -- so every slice gets every P-th hub; the cold part (low-degree nodes clustered next to
+// their first neighbour) is dealt in blocks of DEAL_BLOCK positions, so that the siblings of a cluster stay adjacent
+// and the row that gathers them still reads whole sectors.  Labels stay dense in [0, n); `start[r]` = first label of
+// slice r, `hot_of[r]` = hot nodes in slice r.
+constexpr int DEAL_BLOCK = 64;
+struct DealPlan {
+    int32_t start[17];
+    int32_t hot_of[16];
+};
+__global__ void k_deal_labels(const int32_t* __restrict__ old_of_new_in, int32_t n, int32_t n_hot, int32_t parts, DealPlan plan,
+                              int32_t* __restrict__ old_of_new, int32_t* __restrict__ new_of_old) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int32_t q = n / parts, rem = n % parts, r = i % parts;
-    const int32_t lab = r * q + (r < rem ? r : rem) + i / parts;
+    int32_t lab;
+    if (i < n_hot) {
+        const int32_t r = i % parts;
+        lab = plan.start[r] + i / parts;
+    } else {
+        const int32_t j = i - n_hot, blk = j / DEAL_BLOCK, r = blk % parts;
+        lab = plan.start[r] + plan.hot_of[r] + (blk / parts) * DEAL_BLOCK + j % DEAL_BLOCK;
+    }
     const int32_t o = old_of_new_in[i];
     old_of_new[lab] = o;
     new_of_old[o] = lab;
@@ -500,20 +513,30 @@ static void graph_build_impl(rwr_graph* g) {
         KERNEL_CHECK();
     }
 
-    // ---- row-partitioned graph: interleave the label order over the slices (see k_interleave_labels)
+    // ---- row-partitioned graph: deal the label order over the slices (see k_deal_labels)
     {
         const int parts = dist_n_ranks(g->comm);
         if (parts > 1 && n > 0) {
+            if (parts > 16) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 16 ranks");
+            const int32_t n_hot = g->relabelled ? g->n_hot : n;       // without a relabel every position is dealt singly
+            DealPlan plan;
+            int32_t cold_of[16];
+            const int32_t n_cold = n - n_hot, full_blocks = n_cold / DEAL_BLOCK, tail = n_cold % DEAL_BLOCK;
+            for (int r = 0; r < parts; r++) {
+                plan.hot_of[r] = n_hot / parts + (r < n_hot % parts ? 1 : 0);
+                cold_of[r] = (full_blocks / parts + (r < full_blocks % parts ? 1 : 0)) * DEAL_BLOCK;
+            }
+            cold_of[full_blocks % parts] += tail;                      // the partial last block goes to the next slice in turn
+            plan.start[0] = 0;
+            for (int r = 0; r < parts; r++) plan.start[r + 1] = plan.start[r] + plan.hot_of[r] + cold_of[r];
             g->n_hot = n;                             // hotness is no longer a label prefix
             DevBuf<int32_t> tmp;
             tmp.alloc(n);
             CUDA_CHECK(cudaMemcpyAsync(tmp.p, g->old_of_new.p, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
-            k_interleave_labels<<<grid_for(n), 256, 0, st>>>(tmp.p, n, parts, g->old_of_new.p, g->new_of_old.p);
+            k_deal_labels<<<grid_for(n), 256, 0, st>>>(tmp.p, n, n_hot, parts, plan, g->old_of_new.p, g->new_of_old.p);
             KERNEL_CHECK();
             CUDA_CHECK(cudaStreamSynchronize(st));
-            g->part_rows.resize((size_t)parts + 1);
-            const int32_t q = n / parts, rem = n % parts;
-            for (int r = 0; r <= parts; r++) g->part_rows[r] = r * q + std::min<int32_t>(r, rem);
+            g->part_rows.assign(plan.start, plan.start + parts + 1);
         }
     }
 

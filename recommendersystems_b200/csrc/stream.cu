@@ -166,6 +166,9 @@ int ws_hub_entries(const rwr_graph* g, int precision) {
     long cap = (long)(((size_t)g->max_smem_optin - WS_HDR) / elt) & ~3L;
     const long auto_cap = (long)(((precision == RWR_FP32 ? WS_HUB_AUTO_BYTES_FP32 : WS_HUB_AUTO_BYTES) - WS_HDR) / elt) & ~3L;
     long want = g->opts.hub_entries < 0 ? std::min(cap, auto_cap) : std::min<long>(cap, (long)g->opts.hub_entries & ~3L);
+    // when x is far beyond L2 (or the labels are dealt over the slices of a partitioned graph, where the hottest sources
+    // are no longer a label prefix) the table is not worth the L1 it takes: big_x_probe.py, +12 % in FP32 without it
+    if (g->opts.hub_entries < 0 && ((size_t)g->n * elt > ((size_t)160 << 20) || dist_n_ranks(g->comm) > 1)) want = 0;
     long n4 = ((long)g->n + 3) & ~3L;
     return (int)std::max<long>(0, std::min(want, n4));
 }
