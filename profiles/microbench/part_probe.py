@@ -16,7 +16,7 @@ else:
     spec = bench.scaled_spec(float(sys.argv[1]) if len(sys.argv) > 1 else 1.0)
 import time
 t0 = time.perf_counter()
-g = rs.Graph.synthetic(spec, comm=comm); g.buildGraph()
+g = rs.Graph.synthetic(spec, comm=comm, hub_entries=int(os.environ.get("HUB", "-1"))); g.buildGraph()
 torch.cuda.synchronize()
 if rank == 0: sys.stdout.write(f"setup wall {time.perf_counter() - t0:.1f} s synth {g.info().synth_ms:.0f} ms build {g.info().build_ms:.0f} ms\n"); sys.stdout.flush()
 i = g.info()

@@ -233,6 +233,7 @@ constexpr int DEAL_BLOCK = 64;
 struct DealPlan {
     int32_t start[17];
     int32_t hot_of[16];
+    int32_t block;
 };
 __global__ void k_deal_labels(const int32_t* __restrict__ old_of_new_in, int32_t n, int32_t n_hot, int32_t parts, DealPlan plan,
                               int32_t* __restrict__ old_of_new, int32_t* __restrict__ new_of_old) {
@@ -243,8 +244,8 @@ __global__ void k_deal_labels(const int32_t* __restrict__ old_of_new_in, int32_t
         const int32_t r = i % parts;
         lab = plan.start[r] + i / parts;
     } else {
-        const int32_t j = i - n_hot, blk = j / DEAL_BLOCK, r = blk % parts;
-        lab = plan.start[r] + plan.hot_of[r] + (blk / parts) * DEAL_BLOCK + j % DEAL_BLOCK;
+        const int32_t j = i - n_hot, blk = j / plan.block, r = blk % parts;
+        lab = plan.start[r] + plan.hot_of[r] + (blk / parts) * plan.block + j % plan.block;
     }
     const int32_t o = old_of_new_in[i];
     old_of_new[lab] = o;
@@ -521,10 +522,12 @@ static void graph_build_impl(rwr_graph* g) {
             const int32_t n_hot = g->relabelled ? g->n_hot : n;       // without a relabel every position is dealt singly
             DealPlan plan;
             int32_t cold_of[16];
-            const int32_t n_cold = n - n_hot, full_blocks = n_cold / DEAL_BLOCK, tail = n_cold % DEAL_BLOCK;
+            const char* eb = getenv("RWR_DEAL_BLOCK");
+            plan.block = eb ? std::max(1, atoi(eb)) : DEAL_BLOCK;
+            const int32_t n_cold = n - n_hot, full_blocks = n_cold / plan.block, tail = n_cold % plan.block;
             for (int r = 0; r < parts; r++) {
                 plan.hot_of[r] = n_hot / parts + (r < n_hot % parts ? 1 : 0);
-                cold_of[r] = (full_blocks / parts + (r < full_blocks % parts ? 1 : 0)) * DEAL_BLOCK;
+                cold_of[r] = (full_blocks / parts + (r < full_blocks % parts ? 1 : 0)) * plan.block;
             }
             cold_of[full_blocks % parts] += tail;                      // the partial last block goes to the next slice in turn
             plan.start[0] = 0;
