@@ -340,6 +340,8 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
     g = rs.Graph.synthetic(spec, comm=comm)
     g.buildGraph()
     info = g.info()
+    # a collective call needs the SAME seed on every rank: the raw links are replicated, so every rank picks the same user
+    seed = int(pick_seeds(g.degrees(raw=True), spec["n_users"], 1)[0])
     vb = 4 if precision == rs.FP32 else 8
     m = run_fixed(g, [seed], c, N_ITER, precision)
     m.rerun([seed], c, N_ITER)
@@ -373,7 +375,7 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
             "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1), "device_bytes": info.device_bytes},
             "nvlink": {"achieved_lower_bound": round(gathered / (per_iter_ms * 1e-3) / 1e9, 1), "peak": 900.0, "unit": "GB/s",
                        "note": "bytes received per rank / whole iteration time (SpMV slice + epilogue with peer stores + allReduce)"},
-            "top10_head": top[:3]}
+            "seed": seed, "top10_head": top[:3]}
 
 
 def cpu_baseline_leg(g, seed: int, nnz: int, sample_iters: int):
