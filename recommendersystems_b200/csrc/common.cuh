@@ -175,13 +175,6 @@ __device__ __forceinline__ double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
-// fixed-shape tree (deterministic for a given lane assignment)
-template <typename T>
-__device__ __forceinline__ T warp_sum_down(T v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = add_rn(v, __shfl_down_sync(0xffffffffu, v, o));
-    return v;
-}
 
 __device__ __forceinline__ u64 policy_evict_first() {
     u64 pol;
@@ -211,28 +204,12 @@ __device__ __forceinline__ float ld_stream(const float* ptr, u64 pol) {
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ptr), "l"(pol));
     return r;
 }
-__device__ __forceinline__ u32 ld_stream_u32(const u32* ptr, u64 pol) {
-    u32 r;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(ptr), "l"(pol));
-    return r;
-}
 // stores with an L2 eviction policy (streamed results must not push the gathered vector out of L2)
 __device__ __forceinline__ void st_policy(double* ptr, double v, u64 pol) {
     asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(ptr), "d"(v), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void st_policy(float* ptr, float v, u64 pol) {
     asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(ptr), "f"(v), "l"(pol) : "memory");
-}
-// gathered, re-used data: keep in L1 and last to leave L2
-__device__ __forceinline__ double ld_keep(const double* ptr, u64 pol) {
-    double r;
-    asm volatile("ld.global.nc.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(r) : "l"(ptr), "l"(pol));
-    return r;
-}
-__device__ __forceinline__ float ld_keep(const float* ptr, u64 pol) {
-    float r;
-    asm volatile("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(r) : "l"(ptr), "l"(pol));
-    return r;
 }
 
 #endif  // __CUDACC__
