@@ -270,6 +270,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     }
     if (launched > 0) dist_allgather_rows(g, y_out, sizeof(T));       // row-partitioned: every rank gets the whole rank vector
     CUDA_CHECK(cudaEventRecord(ev1, st));
+    if (!iter_ms) return;                          // the caller keeps enqueueing and reads the events after its own sync
     CUDA_CHECK(cudaEventSynchronize(ev1));
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
@@ -387,7 +388,8 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
 // One fixed-iteration run of one seed into a caller-provided rank vector (internal labels); used by the fused
 // request path (rwr_recommend) so that no result object and no cudaMalloc / cudaFree sit on that path.
 template <typename T>
-void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches) {
+void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches,
+                         cudaEvent_t ext0, cudaEvent_t ext1) {
     cudaStream_t st = g->stream;
     const size_t n = (size_t)g->n;
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
@@ -398,19 +400,25 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     const size_t slots = (size_t)g->sm_count * 8 + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);
     ws.ctl.alloc(&g->scratch, 1);
-    cudaEvent_t ev0, ev1;
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev0, cudaEventDefault));
-    CUDA_CHECK(cudaEventCreateWithFlags(&ev1, cudaEventDefault));
     const int64_t l0 = g->pool.launches;
     int it = 0;
     double rs = 0;
-    run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, iter_ms, ev0, ev1);
+    if (ext0 && ext1) {
+        // no host synchronisation: the workspace goes back to the scratch pool while the kernels are still queued, which is
+        // safe because every later user of those blocks enqueues on the same stream
+        run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, nullptr, ext0, ext1);
+    } else {
+        cudaEvent_t ev0, ev1;
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev0, cudaEventDefault));
+        CUDA_CHECK(cudaEventCreateWithFlags(&ev1, cudaEventDefault));
+        run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, iter_ms, ev0, ev1);
+        cudaEventDestroy(ev0);
+        cudaEventDestroy(ev1);
+    }
     *launches += g->pool.launches - l0;
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
 }
-template void iterate_single_into<double>(rwr_graph*, int, double, int, double*, float*, int64_t*);
-template void iterate_single_into<float>(rwr_graph*, int, double, int, float*, float*, int64_t*);
+template void iterate_single_into<double>(rwr_graph*, int, double, int, double*, float*, int64_t*, cudaEvent_t, cudaEvent_t);
+template void iterate_single_into<float>(rwr_graph*, int, double, int, float*, float*, int64_t*, cudaEvent_t, cudaEvent_t);
 
 static int run_entry(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c, int mode, int32_t n_iter, double thr,
                      int32_t max_iter, int32_t precision, int32_t* iters_out, rwr_result** out, rwr_result* reuse = nullptr) {

@@ -395,8 +395,8 @@ static void mark_excluded(rwr_graph* g, int seed, u32* excl, size_t words) {
 
 template <typename T>
 static void topk_one(rwr_graph* g, const T* y, int ld, int seed, int k, u32* excl, size_t words, Cand* block_out, int grid,
-                     int64_t* d_ids, double* d_scores, int* d_count) {
-    mark_excluded(g, seed, excl, words);
+                     int64_t* d_ids, double* d_scores, int* d_count, bool marked = false) {
+    if (!marked) mark_excluded(g, seed, excl, words);
     Scratch<u64> block_max;
     block_max.alloc(&g->scratch, (size_t)grid);
     k_topk_bound<T><<<grid, TOPK_THREADS, 0, g->stream>>>(y, ld, g->node_type_int.p, excl, g->n, block_max.p);
@@ -541,7 +541,8 @@ int spmm_tile_width(int precision);
 void ensure_fp32_arrays(rwr_graph* g);
 
 template <typename T>
-void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches);
+void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches,
+                         cudaEvent_t ext0, cudaEvent_t ext1);
 
 // seeds one by one through the single-column kernel (k <= 16): no result objects, scratch from the handle's pool
 template <typename T>
@@ -564,12 +565,22 @@ static void recommend_singles(rwr_graph* g, const int32_t* seeds, int n_seeds, d
     CUDA_CHECK(cudaMemsetAsync(d_sc.p, 0, (size_t)n_seeds * k * 8, st));
     float it_ms = 0.f;
     int64_t launches = 0;
-    cudaEvent_t e0, e1;
+    struct Events {                                 // destroyed on every exit path (a seed without links throws)
+        cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+        ~Events() { for (auto& x : e) if (x) cudaEventDestroy(x); }
+    } evs;
+    cudaEvent_t &e0 = evs.e[0], &e1 = evs.e[1], &i0 = evs.e[2], &i1 = evs.e[3];
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    // one request (the usual case): the exclusion list first (its host round trip happens before any kernel is queued),
+    // then iterations and top-k enqueued back to back with a single synchronisation at the end
+    const bool one = n_seeds == 1;
+    if (one) { CUDA_CHECK(cudaEventCreate(&i0)); CUDA_CHECK(cudaEventCreate(&i1)); }
     CUDA_CHECK(cudaEventRecord(e0, st));
     for (int s = 0; s < n_seeds; s++) {
-        iterate_single_into<T>(g, seeds[s], c, n_iter, y.p, &it_ms, &launches);
-        topk_one<T>(g, y.p, 1, seeds[s], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k, d_cnt.p + s);
+        if (one) mark_excluded(g, seeds[s], excl.p, words);
+        iterate_single_into<T>(g, seeds[s], c, n_iter, y.p, &it_ms, &launches, i0, i1);
+        topk_one<T>(g, y.p, 1, seeds[s], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)s * k, d_sc.p + (size_t)s * k,
+                    d_cnt.p + s, /*marked=*/one);
         launches += 3;
     }
     CUDA_CHECK(cudaMemcpyAsync(out_ids, d_ids.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
@@ -579,7 +590,7 @@ static void recommend_singles(rwr_graph* g, const int32_t* seeds, int n_seeds, d
     CUDA_CHECK(cudaEventSynchronize(e1));
     float tot = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&tot, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (one) CUDA_CHECK(cudaEventElapsedTime(&it_ms, i0, i1));
     if (info) {
         info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = sizeof(T) == 4 ? RWR_FP32 : RWR_FP64;
         info->iterations = n_iter; info->residual = NAN; info->iterate_ms = it_ms; info->total_ms = tot;
