@@ -68,6 +68,7 @@ struct rwr_graph {
     DevBuf<float> ws_val32;             // lazily built for FP32 runs
     DevBuf<u32> ws_tile;                // [ws_tiles + 1]
     int32_t ws_tiles = 0;
+    int32_t ws_tile_links = 0;          // links per tile of this graph's stream (WS_TILE, or WS_TILE_SMALL for small graphs)
     int64_t ws_nnz = 0;                 // nnz + one padding link per row without in-links
     DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
     DevBuf<u8> node_type_int;

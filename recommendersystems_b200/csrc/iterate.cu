@@ -180,7 +180,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     T* ya = reinterpret_cast<T*>(ws.ya.p);
     IterParams<T> p;
     p.n = n; p.inv = Prec<T>::inv(g);
-    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
+    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles; p.tile_links = g->ws_tile_links;
     p.row_begin = g->row_begin; p.row_end = g->row_end;
     p.omc = (T)(1.0 - c);                                      // Model.cs:84 `(1 - dampingFactor)`
     p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot; p.debug = 0;
@@ -346,7 +346,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     T* ya = reinterpret_cast<T*>(ws.ya.p);
     IterParams<T> p;
     p.n = g->n; p.inv = Prec<T>::inv(g);
-    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles;
+    p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles; p.tile_links = g->ws_tile_links;
     p.row_begin = g->row_begin; p.row_end = g->row_end;
     p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot;
     p.head_partial = ws.head.p; p.carry = ws.carry.p; p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;

@@ -13,6 +13,7 @@ struct IterParams {
     const T* ws_val;        // valued layout only
     const u32* ws_tile;     // [ws_tiles + 1] first row of a tile | continued-row flag in bit 31
     int ws_tiles;
+    int tile_links;         // links per tile
     int row_begin, row_end; // rows of W^T this rank owns ([0, n) unless the graph is row-partitioned)
     int parted;             // row-partitioned: the epilogue leaves its partial sums in ctl->red for the allReduce
     int n_peers;            // peers whose copy of x_next the epilogue writes directly (NVLink peer stores)

@@ -89,11 +89,12 @@ __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ 
     }
 }
 
-__global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, u32 q0, int row_end, int n_tiles, u32* __restrict__ ws_tile) {
+__global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, u32 q0, int row_end, int n_tiles, u32 tile_links,
+                           u32* __restrict__ ws_tile) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t > n_tiles) return;
     if (t == n_tiles) { ws_tile[t] = (u32)row_end; return; }
-    const u32 q = q0 + (u32)t * (u32)WS_TILE;
+    const u32 q = q0 + (u32)t * tile_links;
     const int r = ws_row_of(ptr2, n, q);
     ws_tile[t] = (u32)r | (q > ptr2[r] ? END_BIT : 0u);
 }
@@ -136,8 +137,12 @@ void stream_prepare(rwr_graph* g) {
         q0 = lim[0];
         nnz2 = lim[1] - lim[0];
     }
-    const int n_tiles = (int)(((u64)nnz2 + WS_TILE - 1) / WS_TILE);
-    const size_t padded = (size_t)n_tiles * WS_TILE;
+    // tile size: WS_TILE links, but small graphs (the reference's ego networks) get WS_TILE_SMALL so that their few
+    // hundred thousand links still spread over every SM instead of a couple of them
+    const int tile_links = nnz2 < (u32)WS_SMALL_GRAPH_LINKS ? WS_TILE_SMALL : WS_TILE;
+    g->ws_tile_links = tile_links;
+    const int n_tiles = (int)(((u64)nnz2 + tile_links - 1) / tile_links);
+    const size_t padded = (size_t)n_tiles * tile_links;
     g->ws_nnz = nnz2;
     g->ws_tiles = n_tiles;
     g->ws_src.alloc(padded, &g->pool);
@@ -147,7 +152,7 @@ void stream_prepare(rwr_graph* g) {
     if (padded)
         k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, q0,
                                                       nnz2, padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
-    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, g->ws_tile.p);
+    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, (u32)tile_links, g->ws_tile.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (parts > 1) {          // the whole-graph pull arrays are only needed by the batched path, which a slice does not run
@@ -348,9 +353,10 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
     // link offset of this lane's first int4 in stage st of tile t (tiles past the end re-read the last one)
     auto pos_of = [&](int t, int st) -> size_t {
         t = t < n_tiles ? t : n_tiles - 1;
-        return (size_t)t * WS_TILE + (size_t)(st * WS_STAGE + lane * 4);
+        return (size_t)t * p.tile_links + (size_t)(st * WS_STAGE + lane * 4);
     };
 
+    const int spt = p.tile_links / WS_STAGE;       // stages per tile (even)
     if (cur < n_tiles) {
         const u32 lt = (1u << lane) - 1u, le = lt | (1u << lane);
         // two register stages, A and B, used alternately (the loop is unrolled by two so that no register that is the
@@ -398,7 +404,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
             _Pragma("unroll") for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + POSY + j * WS_STEP, pol_stream, WY[j]); \
         }                                                                                                              \
         WCLK(1);                                                                                                       \
-        POSX = ((ST) + 2 < WS_SPT) ? pos_of(cur, (ST) + 2) : pos_of(nxt, (ST) + 2 - WS_SPT);                           \
+        POSX = ((ST) + 2 < spt) ? pos_of(cur, (ST) + 2) : pos_of(nxt, (ST) + 2 - spt);                                 \
         _Pragma("unroll") for (int j = 0; j < WS_R; j++)                                                               \
             IVX[j] = ld_stream_int4(reinterpret_cast<const int4*>(p.ws_src + POSX + j * WS_STEP), pol_stream);         \
         WCLK(2);                                                                                                       \
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
             ws_consume<T>(p, s, fl, v, lane, lt, le, pol_stream);                                                      \
         }                                                                                                              \
         WCLK(4);                                                                                                       \
-        if ((ST) == WS_SPT - 1) {                                                                                      \
+        if ((ST) == spt - 1) {                                                                                         \
             const double c = s.spread ? warp_sum(s.lane_acc) : __shfl_sync(0xffffffffu, s.lane_acc, 31);               \
             if (lane == 0) p.carry[s.tile] = c;                                                                        \
         }                                                                                                              \
@@ -428,7 +434,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
     }
 
         while (cur < n_tiles) {
-            for (int st = 0; st < WS_SPT; st += 2) {
+            for (int st = 0; st < spt; st += 2) {
                 WS_HALF(st, ivA, gA, wA, posA, ivB, gB, wB, posB)
                 WS_HALF(st + 1, ivB, gB, wB, posB, ivA, gA, wA, posA)
             }
