@@ -137,9 +137,14 @@ void stream_prepare(rwr_graph* g) {
         q0 = lim[0];
         nnz2 = lim[1] - lim[0];
     }
-    // tile size: WS_TILE links, but small graphs (the reference's ego networks) get WS_TILE_SMALL so that their few
-    // hundred thousand links still spread over every SM instead of a couple of them
-    const int tile_links = nnz2 < (u32)WS_SMALL_GRAPH_LINKS ? WS_TILE_SMALL : WS_TILE;
+    // tile size: WS_TILE links, but smaller graphs (the reference's ego networks) get smaller tiles so that their links
+    // still spread over every warp of every SM (big_x_probe.py with RWR_TILE_LINKS: 3.9 M links 39 / 42 / 59 us per
+    // iteration with 512 / 1024 / 4096-link tiles, 19.8 M links 92 / 84 / 96 us, 61 M links 244 / 214 / 208 us)
+    int tile_links = nnz2 < (u32)WS_SMALL_GRAPH_LINKS ? WS_TILE_SMALL : (nnz2 < (u32)WS_MEDIUM_GRAPH_LINKS ? WS_TILE_MEDIUM : WS_TILE);
+    if (const char* et = getenv("RWR_TILE_LINKS")) {            // probe knob: any multiple of 512
+        const int v = atoi(et);
+        if (v >= 512 && v % 512 == 0) tile_links = v;
+    }
     g->ws_tile_links = tile_links;
     const int n_tiles = (int)(((u64)nnz2 + tile_links - 1) / tile_links);
     const size_t padded = (size_t)n_tiles * tile_links;

@@ -10,9 +10,12 @@ constexpr int WS_R = 2;                          // rounds per pipeline stage
 constexpr int WS_STAGE = WS_R * WS_STEP;         // 256 links per stage
 constexpr int WS_TILE = 4096;                    // links per tile (unit of work distribution and of the fix-up)
 constexpr int WS_TILE_SMALL = 512;               // tile size of graphs with fewer than WS_SMALL_GRAPH_LINKS links
-constexpr int WS_SMALL_GRAPH_LINKS = 4 << 20;
+constexpr int WS_TILE_MEDIUM = 1024;             // ... with fewer than WS_MEDIUM_GRAPH_LINKS links
+constexpr int WS_SMALL_GRAPH_LINKS = 8 << 20;
+constexpr int WS_MEDIUM_GRAPH_LINKS = 48 << 20;
 constexpr int WS_SPT = WS_TILE / WS_STAGE;
-static_assert(WS_TILE_SMALL % (2 * WS_STAGE) == 0 && WS_TILE % (2 * WS_STAGE) == 0, "a tile is an even number of stages");       // 32 stages per tile
+static_assert(WS_TILE_SMALL % (2 * WS_STAGE) == 0 && WS_TILE_MEDIUM % (2 * WS_STAGE) == 0 && WS_TILE % (2 * WS_STAGE) == 0,
+              "a tile is an even number of stages");       // 32 stages per tile
 constexpr int WS_HDR = 128;                      // mbarrier, ahead of the hub table
 constexpr int FIN_THREADS = 256;
 constexpr size_t WS_HUB_AUTO_BYTES = 99 * 1024;         // automatic hub size, FP64: fits the 100 KB carve-out step with the 1 KB the system reserves
