@@ -1,26 +1,33 @@
-// stream.cu -- K7 (default, rwr_opts.kernel = 0): warp-streamed SpMV over a flagged edge stream.
+// stream.cu -- K7: the power iteration  r <- (1-c) W^T r + S q  as a warp-streamed SpMV over a flagged edge stream.
 //
-// Restates the push loop of Recommenders/RWRBased/Model.cs:76-100 as a pull over W^T, like iterate.cu, but with a
-// layout and a schedule built around what bounds this kernel on a B200: not HBM bytes but the ~1 scattered gather per
-// cycle per SM the L1TEX path sustains (profiles/microbench/gather_bench.cu: 289 G reads/s from L2, 1500 G reads/s
-// from shared memory).  Everything else is arranged so that the gather queue never runs dry.
+// Restates the push loop of Recommenders/RWRBased/Model.cs:76-100 as a pull over W^T, with a layout and a schedule
+// built around what bounds this kernel on a B200: not HBM bytes but the ~1 scattered gather per cycle per SM that the
+// L1TEX path sustains (profiles/microbench/gather_bench.cu: 289 G reads/s from L2, 1500 G reads/s from shared memory),
+// and the L1 capacity that holds the sectors of the gathers in flight.  Everything else is arranged so that the gather
+// queue never runs dry.  One iteration = three launches:
+//   k_spmv_ws     raw row sums y_t = sum_i x_i over the links of row t (x is pre-scaled: x_i = fl(fl((1-c) r_i) w_i))
+//   k_cutrows_ws  the few rows cut by a tile boundary, assembled from per-tile partial sums in tile order
+//   k_finish_ws   the fused per-row epilogue (restart AXPY, next x, restart-mass and L1-residual partials, their
+//                 fixed-order reduction, the convergence test of Model.cs:110-115) -- streamed and coalesced
 //
 // Layout ("edge stream", built once per graph by stream_prepare):
 //   ws_src[q]   source label of the q-th stored link of W^T, rows back to back; bit 31 set on the LAST link of a row.
 //               A row without in-links gets one padding link to the always-zero entry x[n], so every row owns >= 1
 //               link, row ids are implicit (count the end flags) and y / x_next of such rows are written like any other.
+//               Inside a 256-link stage the links are stored lane-major (a lane owns 8 consecutive links).
 //   ws_val[q]   normalised weight of the link (valued layout only; the index-only layout folds the row's common
 //               weight into x, see graph.cu)
-//   ws_tile[t]  row of the first link of tile t (WS_TILE links) | bit 31 when that row started in an earlier tile
+//   ws_tile[t]  row of the first link of tile t | bit 31 when that row started in an earlier tile.  A tile is 4096 links
+//               (1024 / 512 for graphs under 48 M / 8 M links).
 //
-// Schedule: 16 independent warps per SM, no block-level barrier inside the loop.  A warp walks tiles t = w, w + W, ...
-// in steps of 128 links (one int4 of indices per lane, coalesced, evict-first).  Indices are loaded two steps ahead
-// and the gathers of x are issued one step ahead (branch-free: shared-memory hub table for the hottest sources, L2
-// otherwise), so ~4 k gathers per SM are always in flight.  Row sums: a step without a row end just adds into a
-// per-lane accumulator; a step with row ends runs a warp-level segmented scan (shuffles only), and the lanes holding
-// a row end run the fused epilogue (y, next x, restart mass, L1 residual).  The open row at a tile boundary goes to
-// tail[t] / head[t] and is closed by k_fixup_ws in a fixed order -- no floating-point atomics anywhere, so a run is
-// bit-reproducible; the association of a row sum differs from the reference's sequential one by O(log deg) ulp.
+// Schedule of k_spmv_ws: 16 independent warps per SM (20 in FP32 index-only), no block-level barrier inside the loop.
+// Tiles are handed out dynamically, one atomic per tile drawn a tile ahead.  A warp walks its tile in stages of 256
+// links (two coalesced int4 of indices per lane, evict-first): indices are loaded two stages ahead and the gathers of x
+// one stage ahead -- one generic-address load per link, into the shared-memory hub table (the hottest sources) or L2.
+// Row sums use registers and shuffles only: a stage without a row end adds into a per-lane accumulator; a stage with
+// row ends runs a warp-level segmented scan with early exit, and the lanes holding a row end store the sums.  The open
+// row at a tile boundary goes to tail[t] / head[t].  No floating-point atomics anywhere: a run is bit-reproducible; the
+// association of a row sum differs from the reference's sequential one by O(log deg) ulp (all addends >= 0).
 #include <algorithm>
 #include <cmath>
 
