@@ -61,7 +61,7 @@ typedef struct rwr_opts {
     int32_t device;        /* CUDA ordinal; -1 = current device                                                 */
     int32_t layout;        /* RWR_LAYOUT_*                                                                      */
     int32_t relabel;       /* 0 = auto (on): internal relabel by descending out-degree; 1 = off                 */
-    int32_t hub_entries;   /* x entries staged in shared memory per CTA; -1 = auto, 0 = none                    */
+    int32_t hub_entries;   /* x entries staged in shared memory per CTA; -1 = auto (sized to leave L1 room), 0 = none */
     int32_t batch_width;   /* seed columns per SpMM tile; 0 = auto                                              */
     int32_t kernel;        /* reserved, must be 0 (the warp-streamed edge-stream kernels are the only SpMV path)          */
     uint64_t stream;       /* cudaStream_t to run on (0 = the handle creates its own non-blocking stream)       */
@@ -95,7 +95,7 @@ typedef struct rwr_graph_info {
     int32_t relabelled;
     int32_t n_hot;           /* internal labels [0, n_hot) are the degree-sorted hot nodes                      */
     int32_t hub_entries_fp64, hub_entries_fp32;
-    int32_t n_chunks;        /* merge-path work items of the SpMV                                               */
+    int32_t n_chunks;        /* merge-path work items of the batched (SpMM) kernel                              */
     int32_t max_in_degree, max_out_degree;
     float build_ms;          /* rwr_graph_build device time (CUDA events)                                       */
     float synth_ms;          /* rwr_synth_create device time                                                    */
@@ -173,8 +173,9 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
                   int32_t precision, int32_t k, int64_t* out_ids, double* out_scores, int32_t* out_counts,
                   rwr_run_info* info /* may be NULL */);
 
-/* ---- measurement probe: average device time of the two kernels of one iteration (CUDA events on the handle's
- * stream, `reps` iterations after 3 warm-up iterations).  Used by bench.py for the roofline of k_spmv.      */
+/* ---- measurement probe: average device time of one iteration's kernels (CUDA events on the handle's stream, `reps`
+ * iterations after 3 warm-up iterations): spmv_ms = k_spmv_ws, fixup_ms = k_cutrows_ws + k_finish_ws.  Used by
+ * bench.py for the roofline of the dominant kernel.                                                                  */
 int rwr_profile_iteration(rwr_graph* g, int32_t seed, double c, int32_t precision, int32_t reps, float* spmv_ms,
                           float* fixup_ms);
 
