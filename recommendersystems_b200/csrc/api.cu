@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 static thread_local char g_last_error[1024] = "";
+thread_local cudaStream_t tls_alloc_stream = nullptr;
 
 void rwr_set_error(const char* fmt, ...) {
     va_list ap;

@@ -61,11 +61,26 @@ struct DevPool {
     int64_t launches = 0;   // kernels launched through this handle (bench "gpu_launches")
 };
 
+// Device allocations made while an AllocStream guard is alive on the calling thread come from the device's memory pool,
+// ordered on that stream (cudaMallocAsync / cudaFreeAsync): no device-wide synchronisation on free, and microseconds
+// instead of ~0.1 ms per call -- the reference builds one graph per ego network, from up to ten threads at once.
+// Without a guard (or for buffers marked `plain`, which may outlive the stream) plain cudaMalloc / cudaFree are used.
+extern thread_local cudaStream_t tls_alloc_stream;
+struct AllocStream {
+    cudaStream_t prev;
+    explicit AllocStream(cudaStream_t s) : prev(tls_alloc_stream) { tls_alloc_stream = s; }
+    ~AllocStream() { tls_alloc_stream = prev; }
+    AllocStream(const AllocStream&) = delete;
+    AllocStream& operator=(const AllocStream&) = delete;
+};
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     DevPool* pool = nullptr;
+    cudaStream_t astream = nullptr;   // stream the block was allocated on (pool allocation), null: cudaMalloc
+    bool plain = false;               // always cudaMalloc / cudaFree (the buffer may be freed after its stream is gone)
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
@@ -73,8 +88,8 @@ struct DevBuf {
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
             release();
-            p = o.p; n = o.n; pool = o.pool;
-            o.p = nullptr; o.n = 0;
+            p = o.p; n = o.n; pool = o.pool; astream = o.astream; plain = o.plain;
+            o.p = nullptr; o.n = 0; o.astream = nullptr;
         }
         return *this;
     }
@@ -84,16 +99,23 @@ struct DevBuf {
         pool = pl;
         n = count;
         size_t bytes = (count ? count : 1) * sizeof(T);
-        CUDA_CHECK(cudaMalloc((void**)&p, bytes));
+        if (!plain && tls_alloc_stream) {
+            CUDA_CHECK(cudaMallocAsync((void**)&p, bytes, tls_alloc_stream));
+            astream = tls_alloc_stream;
+        } else {
+            CUDA_CHECK(cudaMalloc((void**)&p, bytes));
+            astream = nullptr;
+        }
         if (pool) pool->bytes += (int64_t)bytes;
     }
     void release() {
         if (p) {
-            cudaFree(p);
+            if (astream) cudaFreeAsync(p, astream); else cudaFree(p);
             if (pool) pool->bytes -= (int64_t)((n ? n : 1) * sizeof(T));
         }
         p = nullptr;
         n = 0;
+        astream = nullptr;
     }
     operator T*() const { return p; }
 };
@@ -101,7 +123,12 @@ struct DevBuf {
 // Per-handle cache of device scratch blocks: request-path workspaces are reused instead of going through
 // cudaMalloc / cudaFree (which synchronise the device) on every call.
 struct ScratchPool {
-    struct Block { void* p; size_t bytes; bool used; };
+    struct Block { void* p; size_t bytes; bool used; cudaStream_t astream; };
+    static cudaError_t raw_alloc(void** p, size_t bytes, cudaStream_t* as) {
+        *as = tls_alloc_stream;
+        return tls_alloc_stream ? cudaMallocAsync(p, bytes, tls_alloc_stream) : cudaMalloc(p, bytes);
+    }
+    static void raw_free(const Block& b) { if (b.astream) cudaFreeAsync(b.p, b.astream); else cudaFree(b.p); }
     std::vector<Block> blocks;
     DevPool* pool = nullptr;
     void* get(size_t bytes) {
@@ -112,18 +139,19 @@ struct ScratchPool {
                 (best < 0 || blocks[i].bytes < blocks[best].bytes)) best = i;
         if (best >= 0) { blocks[best].used = true; return blocks[best].p; }
         void* p = nullptr;
-        cudaError_t err = cudaMalloc(&p, bytes);
+        cudaStream_t as = nullptr;
+        cudaError_t err = raw_alloc(&p, bytes, &as);
         if (err != cudaSuccess) {            // drop every cached free block and retry once
             cudaGetLastError();
             trim();
-            err = cudaMalloc(&p, bytes);
+            err = raw_alloc(&p, bytes, &as);
         }
         if (err != cudaSuccess) {
             rwr_set_error("cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(err));
             throw RwrError{err == cudaErrorMemoryAllocation ? RWR_E_OOM : RWR_E_CUDA};
         }
         if (pool) pool->bytes += (int64_t)bytes;
-        blocks.push_back({p, bytes, true});
+        blocks.push_back({p, bytes, true, as});
         return p;
     }
     void put(void* p) {
@@ -133,11 +161,11 @@ struct ScratchPool {
         std::vector<Block> keep;
         for (auto& b : blocks) {
             if (b.used) keep.push_back(b);
-            else { cudaFree(b.p); if (pool) pool->bytes -= (int64_t)b.bytes; }
+            else { raw_free(b); if (pool) pool->bytes -= (int64_t)b.bytes; }
         }
         blocks.swap(keep);
     }
-    ~ScratchPool() { for (auto& b : blocks) cudaFree(b.p); }
+    ~ScratchPool() { for (auto& b : blocks) raw_free(b); }
 };
 
 template <typename T>

@@ -241,6 +241,7 @@ int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opt
         o.device = comm->device;
         graph_init_device(g, &o);
         g->comm = comm;
+        AllocStream alloc_on(g->stream);
         synth_generate_device(g, spec);
         *out = g;
         return RWR_OK;

@@ -331,6 +331,18 @@ void graph_init_device(rwr_graph* g, const rwr_opts* opts) {
         CUDA_CHECK(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
         g->own_stream = true;
     }
+    // keep up to 2 GB of freed blocks in the device's default memory pool (the default hands everything back at the next
+    // synchronisation, which would make every build re-acquire its temporaries from the driver)
+    cudaMemPool_t mp = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&mp, g->device) == cudaSuccess && mp) {
+        uint64_t thr = 0;
+        if (cudaMemPoolGetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr) == cudaSuccess && thr < ((uint64_t)2 << 30)) {
+            thr = (uint64_t)2 << 30;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
+    } else {
+        cudaGetLastError();
+    }
 }
 
 // Canonicalise the raw links: stable sort by source when needed, then raw_ptr.
@@ -380,6 +392,7 @@ static void graph_build_impl(rwr_graph* g) {
     if (g->built) RWR_FAIL(RWR_E_ALREADY_BUILT, "buildGraph() called twice (ArgumentException at Graph.cs:86)");
     CUDA_CHECK(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
+    AllocStream alloc_on(st);
     const size_t e0 = (size_t)g->e0;
     const int32_t n = g->n;
     cudaEvent_t ev0, ev1;
@@ -623,6 +636,7 @@ int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t
     graph_init_device(g, opts);
     g->comm = comm;
     cudaStream_t st = g->stream;
+    AllocStream alloc_on(st);
     g->n = n_nodes;
     g->e0 = n_links;
     const size_t n = (size_t)n_nodes, e0 = (size_t)n_links;
@@ -775,8 +789,11 @@ void rwr_graph_destroy(rwr_graph* g) {
     if (g->stream) cudaStreamSynchronize(g->stream);
     dist_release_p2p(g);
     for (auto& ig : g->iter_graph) if (ig.exec) cudaGraphExecDestroy(ig.exec);
-    if (g->own_stream && g->stream) cudaStreamDestroy(g->stream);
-    delete g;
+    const cudaStream_t st = g->stream;
+    const bool own = g->own_stream;
+    delete g;                                    // the buffers go back to the pool on the stream ...
+    if (st) cudaStreamSynchronize(st);
+    if (own && st) cudaStreamDestroy(st);        // ... which is destroyed last
 }
 
 }  // extern "C"

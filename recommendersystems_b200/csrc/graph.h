@@ -90,6 +90,7 @@ struct rwr_graph {
     // graphs (the reference's ego networks are a few thousand nodes) are launch-bound otherwise.  One per precision.
     struct IterGraph {
         cudaGraphExec_t exec = nullptr;
+        bool seen = false;              // the key below was used by a direct run; the next identical run captures
         int n_iter = 0, hub = 0;
         double c = 0.0;
         const void* ptr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -709,6 +709,7 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
     if (n_seeds == 0) return RWR_OK;
     if (n_iter < 0) n_iter = 0;
     CUDA_CHECK(cudaSetDevice(g->device));
+    AllocStream alloc_on(g->stream);
     bool all_regular = true;
     for (int s = 0; s < n_seeds; s++) {
         if (seeds[s] < -1 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);

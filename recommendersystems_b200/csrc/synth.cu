@@ -220,6 +220,7 @@ extern "C" int rwr_synth_create(const rwr_synth_spec* spec, const rwr_opts* opts
         *out = nullptr;
         g = new rwr_graph();
         graph_init_device(g, opts);
+        AllocStream alloc_on(g->stream);
         synth_generate_device(g, spec);
         *out = g;
         return RWR_OK;
