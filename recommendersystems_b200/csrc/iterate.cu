@@ -210,26 +210,14 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
             }
         };
         static const bool no_graph = getenv("RWR_NO_GRAPH") != nullptr;
-        if (n_iter >= 2 && dist_n_ranks(g->comm) == 1 && !no_graph) {
-            // replay (or capture once) the graph of the whole loop; nothing in it depends on the seed
-            rwr_graph::IterGraph& ig = g->iter_graph[Prec<T>::id];
-            const void* key[8] = {xa, xb, y_out, ws.ctl.p, ws.head.p, ws.carry.p, ws.slot_S.p, ws.slot_R.p};
-            const bool same = ig.n_iter == n_iter && ig.hub == hub && ig.c == c && memcmp(ig.ptr, key, sizeof(key)) == 0;
-            const bool hit = ig.exec && same;
-            if (!hit && !(ig.seen && same)) {
-                // first run with this key: launch directly and remember the key -- capturing and instantiating costs more
-                // than one run saves, and the reference asks each graph for a single recommendation (Experiment.cs:109)
-                if (ig.exec) { cudaGraphExecDestroy(ig.exec); ig.exec = nullptr; }
-                ig.seen = true; ig.n_iter = n_iter; ig.hub = hub; ig.c = c;
-                memcpy(ig.ptr, key, sizeof(key));
-                launch_all();
-                launched = n_iter;
-                *iters_out = n_iter;
-                *resid_out = NAN;
-                goto fixed_done;
-            }
-            if (!hit) {
-                if (ig.exec) { cudaGraphExecDestroy(ig.exec); ig.exec = nullptr; }
+        rwr_graph::IterGraph& ig = g->iter_graph[Prec<T>::id];
+        const void* key[8] = {xa, xb, y_out, ws.ctl.p, ws.head.p, ws.carry.p, ws.slot_S.p, ws.slot_R.p};
+        const bool graphable = n_iter >= 2 && dist_n_ranks(g->comm) == 1 && !no_graph;
+        const bool same = ig.n_iter == n_iter && ig.hub == hub && ig.c == c && memcmp(ig.ptr, key, sizeof(key)) == 0;
+        if (graphable && same && (ig.exec || ig.seen)) {
+            // second and later runs with this key: replay the graph of the whole loop (captured now if this is the second
+            // run); nothing in it depends on the seed
+            if (!ig.exec) {
                 const int64_t counted = g->pool.launches;
                 cudaGraph_t graph = nullptr;
                 CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -245,18 +233,22 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
                 cudaGraphDestroy(graph);
                 if (err != cudaSuccess) { ig.exec = nullptr; CUDA_CHECK(err); }
                 g->pool.launches = counted;
-                ig.n_iter = n_iter; ig.hub = hub; ig.c = c;
-                memcpy(ig.ptr, key, sizeof(key));
             }
             CUDA_CHECK(cudaGraphLaunch(ig.exec, st));
             g->pool.launches += 3 * (int64_t)n_iter;
         } else {
+            // first run with this key (or no graph at all): launch kernel by kernel.  Capturing and instantiating costs more
+            // than one run saves, and the reference asks each graph for a single recommendation (Experiment.cs:109).
+            if (graphable) {
+                if (ig.exec) { cudaGraphExecDestroy(ig.exec); ig.exec = nullptr; }
+                ig.seen = true; ig.n_iter = n_iter; ig.hub = hub; ig.c = c;
+                memcpy(ig.ptr, key, sizeof(key));
+            }
             launch_all();
         }
         launched = n_iter;
         *iters_out = n_iter;
         *resid_out = NAN;
-    fixed_done:;
     } else {
         // Model.cs:57-66.  Launch in batches; converged launches are no-ops, the flag is read between batches.
         IterCtl h{};
