@@ -360,7 +360,6 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     { const char* dm = getenv("RWR_DEBUG_MODE"); p.debug = dm ? atoi(dm) : 0; }
     k_init<T><<<div_up(std::max((int)n, 1), 256), 256, 0, st>>>((int)n, seed_int, p.omc, p.inv, ya, xa, xb, ws.ctl.p, 0.0);
     KERNEL_CHECK();
-    const bool valued = g->layout == RWR_LAYOUT_VALUED;
     std::vector<cudaEvent_t> ev(3 * (size_t)reps);
     for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
     T* x_cur = xa;
@@ -396,7 +395,6 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
 template <typename T>
 void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y_out, float* iter_ms, int64_t* launches,
                          cudaEvent_t ext0, cudaEvent_t ext1) {
-    cudaStream_t st = g->stream;
     const size_t n = (size_t)g->n;
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;

@@ -15,8 +15,7 @@ constexpr int MM_GROUPS = 8;
 constexpr int MM_THREADS = MM_GROUPS * GROUP_THREADS;     // 1024
 constexpr int MM_QUADS = GROUP_THREADS / 4;               // 32 rows in flight per group
 constexpr int MM_LONG = 32, MM_HUGE = 256;
-constexpr int MM_LONG_CAP = CHUNK_ITEMS / MM_LONG + 1;    // 32
-constexpr int MM_HUGE_CAP = CHUNK_ITEMS / MM_HUGE + 2;    // 5
+static_assert(CHUNK_ITEMS / MM_LONG + 1 <= 32 && CHUNK_ITEMS / MM_HUGE + 2 <= 8, "capacity of the per-group row lists");
 constexpr int MM_MAXB = 16;
 
 template <typename T> struct Vec;

@@ -335,9 +335,10 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
     u32 smem0;
     asm volatile("{ .reg .u64 t; cvta.to.shared.u64 t, %1; cvt.u32.u64 %0, t; }" : "=r"(smem0) : "l"(smem_raw));
     const u32 hub_addr = smem0 + WS_HDR;
-    u64 hub_gen;                                   // generic address of the hub table, opaque to ptxas (see iterate.cu)
+    u64 hub_gen;                                   // generic address of the hub table, opaque to ptxas (a plain cvta result
+                                                   // is rematerialised at every use)
     asm volatile("mov.u64 %0, %1;" : "=l"(hub_gen) : "l"(smem_raw + WS_HDR));
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
 
     if (threadIdx.x == 0) mbar_init(reinterpret_cast<u64*>(smem_raw), 1);
     __syncthreads();
