@@ -20,6 +20,24 @@ namespace Recommenders.RWRBased.Native {
     }
 
     [StructLayout(LayoutKind.Sequential)]
+    public struct RwrSynthSpec {
+        public ulong seed;
+        public int n_users, n_items, n_third, authorship_per_mille;
+        public long n_like, n_friend, n_follow, n_mention;
+        public int undefined_per_mille, scramble, p1_byte, reserved;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct RwrGraphInfo {
+        public int n_nodes, built;
+        public long n_links_raw, nnz;
+        public int n_dangling, layout, relabelled, n_hot, hub_entries_fp64, hub_entries_fp32, n_chunks, max_in_degree, max_out_degree;
+        public float build_ms, synth_ms;
+        public long device_bytes;
+        public int row_begin, row_end, n_ranks, reserved;
+    }
+
+    [StructLayout(LayoutKind.Sequential)]
     public struct RwrRunInfo {
         public int n_seeds, n_nodes, precision, iterations;
         public double residual;
@@ -48,7 +66,11 @@ namespace Recommenders.RWRBased.Native {
 
         [DllImport(Lib)] public static extern int rwr_graph_create(int nNodes, long[] nodeId, int[] nodeType, long nLinks,
             int[] src, int[] dst, int[] etype, double[] w, ref RwrOpts opts, out GraphHandle graph);
+        [DllImport(Lib)] public static extern int rwr_synth_create(ref RwrSynthSpec spec, ref RwrOpts opts, out GraphHandle graph);
         [DllImport(Lib)] public static extern int rwr_graph_build(GraphHandle g);
+        [DllImport(Lib)] public static extern int rwr_graph_get_info(GraphHandle g, out RwrGraphInfo info);
+        [DllImport(Lib)] public static extern int rwr_graph_export_links(GraphHandle g, long[] nodeId, int[] nodeType, int[] src,
+            int[] dst, int[] etype, double[] w);
         [DllImport(Lib)] public static extern int rwr_graph_get_csr(GraphHandle g, long[] rowPtr, int[] col, double[] val);
         [DllImport(Lib)] public static extern int rwr_graph_get_degrees(GraphHandle g, int[] outDegree, int[] rawDegree);
         [DllImport(Lib)] public static extern void rwr_graph_destroy(IntPtr g);
@@ -69,6 +91,17 @@ namespace Recommenders.RWRBased.Native {
             int precision, int k, long[] outIds, double[] outScores, int[] outCounts, out RwrRunInfo info);
         [DllImport(Lib)] public static extern int rwr_evaluate(long[] rankedIds, long n, long[] testIds, long nTest, out int hits,
             out double avgPrecision);
+        [DllImport(Lib)] public static extern int rwr_profile_iteration(GraphHandle g, int seed, double c, int precision, int reps,
+            out float spmvMs, out float fixupMs);
+
+        // row-partitioned mode: one process per GPU; the 128-byte id goes from rank 0 to the other ranks by any channel
+        [DllImport(Lib)] public static extern int rwr_comm_unique_id(byte[] id128);
+        [DllImport(Lib)] public static extern int rwr_comm_create(int rank, int nRanks, byte[] id128, ref RwrOpts opts, out IntPtr comm);
+        [DllImport(Lib)] public static extern void rwr_comm_destroy(IntPtr comm);
+        [DllImport(Lib)] public static extern int rwr_synth_create_partitioned(ref RwrSynthSpec spec, ref RwrOpts opts, IntPtr comm,
+            out GraphHandle graph);
+        [DllImport(Lib)] public static extern int rwr_graph_create_partitioned(int nNodes, long[] nodeId, int[] nodeType, long nLinks,
+            int[] src, int[] dst, int[] etype, double[] w, ref RwrOpts opts, IntPtr comm, out GraphHandle graph);
 
         public static string LastError() { return Marshal.PtrToStringAnsi(rwr_last_error()) ?? ""; }
 
