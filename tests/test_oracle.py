@@ -170,3 +170,27 @@ def test_evaluate_matches_python():
         want = R.evaluate(rec, test)
         got = O.evaluate([p[0] for p in rec], sorted(test))
         assert got[0] == want[0] and got[1] == want[1]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_fixed_point_is_the_closed_form(name):
+    """An independent check of the iteration itself (not of its rounding): with A = (1-c) W^T restricted to nodes that
+    have out-links, Model.cs:76-100 is r <- A r + q * 1^T (I - A) r, so the limit is proportional to (I - A)^-1 q and
+    carries the initial mass N (Model.cs:41). 300 iterations leave 0.85^300 of the transient."""
+    g = load_golden(name)
+    og = make(g)
+    rp, col, val = og.csr()
+    n = len(rp) - 1
+    c = float.fromhex(g["damping_double"])
+    A = np.zeros((n, n))
+    for i in range(n):
+        for e in range(rp[i], rp[i + 1]):
+            A[col[e], i] += (1 - c) * val[e]
+    for e in g["seeds"]:
+        q = np.zeros(n)
+        q[e["seed"]] = 1.0
+        r = np.linalg.solve(np.eye(n) - A, q)
+        r *= n / r.sum()
+        rank, _ = og.run(e["seed"], c, n_iter=300)
+        assert abs(rank.sum() - n) < 1e-9 * n
+        assert np.allclose(rank, r, rtol=1e-9, atol=1e-12), (name, e["seed"])
