@@ -181,6 +181,16 @@ struct Scratch {
     operator T*() const { return p; }
 };
 
+// CUDA event destroyed on every exit of its scope (error paths throw through the C-ABI guard)
+struct DevEvent {
+    cudaEvent_t e = nullptr;
+    DevEvent() { CUDA_CHECK(cudaEventCreate(&e)); }
+    ~DevEvent() { if (e) cudaEventDestroy(e); }
+    DevEvent(const DevEvent&) = delete;
+    DevEvent& operator=(const DevEvent&) = delete;
+    operator cudaEvent_t() const { return e; }
+};
+
 static inline unsigned div_up(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 static inline int ceil_log2_u64(u64 n) {
     int L = 0;

@@ -395,10 +395,13 @@ static void graph_build_impl(rwr_graph* g) {
     AllocStream alloc_on(st);
     const size_t e0 = (size_t)g->e0;
     const int32_t n = g->n;
-    cudaEvent_t ev0, ev1;
-    CUDA_CHECK(cudaEventCreate(&ev0));
-    CUDA_CHECK(cudaEventCreate(&ev1));
-    CUDA_CHECK(cudaEventRecord(ev0, st));
+    struct Events {                              // destroyed on every exit, including a failed build
+        cudaEvent_t a = nullptr, b = nullptr;
+        ~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    } ev;
+    CUDA_CHECK(cudaEventCreate(&ev.a));
+    CUDA_CHECK(cudaEventCreate(&ev.b));
+    CUDA_CHECK(cudaEventRecord(ev.a, st));
 
     DevBuf<BuildStats> stats;
     stats.alloc(1);
@@ -598,11 +601,9 @@ static void graph_build_impl(rwr_graph* g) {
     iterate_prepare(g);
     dist_setup_p2p(g);
 
-    CUDA_CHECK(cudaEventRecord(ev1, st));
-    CUDA_CHECK(cudaEventSynchronize(ev1));
-    CUDA_CHECK(cudaEventElapsedTime(&g->build_ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
+    CUDA_CHECK(cudaEventRecord(ev.b, st));
+    CUDA_CHECK(cudaEventSynchronize(ev.b));
+    CUDA_CHECK(cudaEventElapsedTime(&g->build_ms, ev.a, ev.b));
     g->built = true;
 }
 
@@ -675,6 +676,7 @@ int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t
     return RWR_OK;
     }
     catch (const RwrError& e__) { rwr_graph_destroy(g); return e__.code; }
+    catch (const std::bad_alloc&) { rwr_graph_destroy(g); rwr_set_error("host allocation failed"); return RWR_E_OOM; }
     catch (...) { rwr_graph_destroy(g); rwr_set_error("unexpected exception"); return RWR_E_INVALID; }
 }
 

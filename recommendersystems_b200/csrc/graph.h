@@ -3,9 +3,9 @@
 
 #include "common.cuh"
 
-// Merge-path work item geometry of the SpMV (iterate.cu).  One chunk = CHUNK_ITEMS path items (rows + nnz),
-// so a chunk holds at most CHUNK_ITEMS non-zeros; with the <= 3 alignment slack of the int4 index loads its
-// span fits the CHUNK_SPAN-entry product buffer.
+// Merge-path work item geometry of the batched SpMM (spmm.cu; the table is built by k_partition in iterate.cu).  One
+// chunk = CHUNK_ITEMS path items (rows + nnz), so a chunk holds at most CHUNK_ITEMS non-zeros; with the <= 3 alignment
+// slack of the int4 index loads its span fits the CHUNK_SPAN-entry index buffer.
 constexpr int GROUP_THREADS = 128;
 constexpr int CHUNK_ROUNDS = 2;                                   // int4 index loads per thread per chunk
 constexpr int CHUNK_SPAN = GROUP_THREADS * 4 * CHUNK_ROUNDS;      // 1024
@@ -84,7 +84,6 @@ struct rwr_graph {
     bool p2p = false;
     void* px[2] = {nullptr, nullptr};     // (n + 8) * 8 bytes each, cudaMalloc
     std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
-
 
     // fixed-count runs replay a captured CUDA graph of their n_iter x (k_spmv_ws, k_cutrows_ws, k_finish_ws) launches: small
     // graphs (the reference's ego networks are a few thousand nodes) are launch-bound otherwise.  One per precision.

@@ -305,9 +305,7 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
     CUDA_CHECK(cudaMemsetAsync(ws.slot_R.p, 0, slots * sizeof(double), st));
     ws.ctl.alloc(&g->scratch, 1);
     CUDA_CHECK(cudaMemsetAsync(ws.ctl.p, 0, sizeof(IterCtl), st));
-    cudaEvent_t ev0, ev1, evA, evB;
-    CUDA_CHECK(cudaEventCreate(&ev0)); CUDA_CHECK(cudaEventCreate(&ev1));
-    CUDA_CHECK(cudaEventCreate(&evA)); CUDA_CHECK(cudaEventCreate(&evB));
+    DevEvent ev0, ev1, evA, evB;
     const int64_t launches0 = g->pool.launches;
     CUDA_CHECK(cudaEventRecord(evA, st));
     res->iterate_ms = 0.f;
@@ -324,7 +322,6 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
     CUDA_CHECK(cudaEventSynchronize(evB));
     CUDA_CHECK(cudaEventElapsedTime(&res->total_ms, evA, evB));
     res->launches = g->pool.launches - launches0;
-    cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(evA); cudaEventDestroy(evB);
 }
 
 template <typename T>
@@ -360,8 +357,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     { const char* dm = getenv("RWR_DEBUG_MODE"); p.debug = dm ? atoi(dm) : 0; }
     k_init<T><<<div_up(std::max((int)n, 1), 256), 256, 0, st>>>((int)n, seed_int, p.omc, p.inv, ya, xa, xb, ws.ctl.p, 0.0);
     KERNEL_CHECK();
-    std::vector<cudaEvent_t> ev(3 * (size_t)reps);
-    for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+    std::vector<DevEvent> ev(3 * (size_t)reps);
     T* x_cur = xa;
     T* x_nxt = xb;
     for (int it = 0; it < 3 + reps; it++) {
@@ -384,7 +380,6 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
         CUDA_CHECK(cudaEventElapsedTime(&m2, ev[3 * r + 1], ev[3 * r + 2]));
         a += m1; b += m2;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
     *spmv_ms = (float)(a / reps);
     *fixup_ms = (float)(b / reps);
     g->pool.launches += 1 + 2 * (3 + reps);
@@ -412,12 +407,8 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
         // safe because every later user of those blocks enqueues on the same stream
         run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, nullptr, ext0, ext1);
     } else {
-        cudaEvent_t ev0, ev1;
-        CUDA_CHECK(cudaEventCreateWithFlags(&ev0, cudaEventDefault));
-        CUDA_CHECK(cudaEventCreateWithFlags(&ev1, cudaEventDefault));
+        DevEvent ev0, ev1;
         run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, iter_ms, ev0, ev1);
-        cudaEventDestroy(ev0);
-        cudaEventDestroy(ev1);
     }
     *launches += g->pool.launches - l0;
 }

@@ -637,8 +637,7 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
     Scratch<int> tile_cnt;                         // [TILE_MAXB] candidate counts | [TILE_MAXB] seeds without links
     excl_t.alloc(&g->scratch, (size_t)B * words); tile_max.alloc(&g->scratch, (size_t)grid * B); tile_bound.alloc(&g->scratch, TILE_MAXB);
     tile_cand.alloc(&g->scratch, (size_t)B * TILE_CAND_CAP); tile_cnt.alloc(&g->scratch, 2 * TILE_MAXB);
-    cudaEvent_t e0, e1, e2;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1)); CUDA_CHECK(cudaEventCreate(&e2));
+    DevEvent e0, e1, e2;
     int64_t launches = 0;
     float it_ms = 0.f, tot_ms = 0.f;
     for (int s0 = 0; s0 < n_seeds; s0 += B) {
@@ -688,7 +687,6 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
     CUDA_CHECK(cudaMemcpyAsync(out_scores, d_sc.p, (size_t)n_seeds * k * 8, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaMemcpyAsync(out_counts, d_cnt.p, (size_t)n_seeds * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     if (info) {
         info->n_seeds = n_seeds; info->n_nodes = g->n; info->precision = sizeof(T) == 4 ? RWR_FP32 : RWR_FP64;
         info->iterations = n_iter; info->residual = NAN; info->iterate_ms = it_ms; info->total_ms = tot_ms;

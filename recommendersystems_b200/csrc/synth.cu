@@ -156,9 +156,7 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec) {
     const size_t slots = (size_t)(2 * s.nrel);
     if (slots >= (1ULL << 32) - 65536) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 link slots per device");
 
-    cudaEvent_t ev0, ev1;
-    CUDA_CHECK(cudaEventCreate(&ev0));
-    CUDA_CHECK(cudaEventCreate(&ev1));
+    DevEvent ev0, ev1;
     CUDA_CHECK(cudaEventRecord(ev0, st));
 
     g->n = (int32_t)N;
@@ -209,8 +207,6 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec) {
     CUDA_CHECK(cudaEventRecord(ev1, st));
     CUDA_CHECK(cudaEventSynchronize(ev1));
     CUDA_CHECK(cudaEventElapsedTime(&g->synth_ms, ev0, ev1));
-    cudaEventDestroy(ev0);
-    cudaEventDestroy(ev1);
 }
 
 extern "C" int rwr_synth_create(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_graph** out) {
