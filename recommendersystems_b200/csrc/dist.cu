@@ -1,12 +1,16 @@
 // dist.cu -- K10: row-partitioned mode for one graph spread over several GPUs (no reference analogue).
 //
 // Every rank owns a contiguous block of rows of W^T (the destination nodes) with its own edge stream (stream.cu).  The
-// internal labels are dealt round-robin over the slices (graph.cu), so the blocks hold equal row counts and, every
-// P-th node of the degree order each, near-equal link counts: both the SpMV and the exchange are balanced.  An iteration on a rank needs the whole gather vector x and produces the slice of the next
-// one for its rows, so after every iteration the slices are allGathered over NVLink / NVSwitch (one grouped set of
-// in-place ncclBroadcast calls: slices have unequal lengths) and the two scalars every rank needs -- the restart mass S
-// and the L1 residual -- are summed with a 16-byte ncclAllReduce.  NCCL is bound at run time (dlopen) so that a
-// single-GPU host needs no NCCL at all.
+// internal labels are dealt over the slices (k_deal_labels, graph.cu): hot nodes one by one, clustered cold nodes in
+// blocks, so the slices hold near-equal row counts and near-equal link counts and both the SpMV and the exchange are
+// balanced.  An iteration on a rank needs the whole gather vector x and produces the slice of the next one for its rows:
+//   * peer path (default, up to 8 ranks): the two gather vectors of every rank are mapped into every other rank through
+//     CUDA IPC, and k_finish_ws stores each new entry into all copies over NVLink / NVSwitch while it computes it;
+//   * NCCL path (fallback: RWR_DIST_NO_P2P=1, more than 8 ranks, or a mapping that fails on any rank): one grouped set
+//     of in-place ncclBroadcast calls per iteration (the slices have unequal lengths).
+// Either way the two scalars every rank needs -- the restart mass S and the L1 residual -- are summed with one 16-byte
+// ncclAllReduce, which is also the barrier that orders the peer stores of one iteration before the gathers of the next.
+// NCCL is bound at run time (dlopen) so that a single-GPU host needs no NCCL at all.
 #include <dlfcn.h>
 
 #include <mutex>

@@ -463,6 +463,10 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
 #ifdef RWR_PROFILE_CLOCKS
         if (clk_sink == -1.0) p.carry[0] = clk_sink;
 #endif
+    } else if (p.hub > 0 && threadIdx.x == 0) {
+        // the thread that issued the bulk copies drew no tile (every tile was taken before this CTA started): a CTA must
+        // not exit with a copy into its shared memory still in flight
+        mbar_wait_a(smem0, 0);
     }
 }
 
