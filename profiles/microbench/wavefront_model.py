@@ -34,6 +34,9 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 C2_SPEC = dict(seed=20260102, n_users=1_000_000, n_items=10_000_000, n_third=0, authorship_per_mille=1000,
                n_like=76_000_000, n_friend=21_000_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
                p1_byte=61, reserved=0)
+C4_SPEC = dict(seed=20260104, n_users=5_000_000, n_items=45_000_000, n_third=0, authorship_per_mille=1000,
+               n_like=700_000_000, n_friend=200_000_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
+               p1_byte=61, reserved=0)
 HOT_MIN = 8
 STAGE = 256
 
@@ -80,6 +83,18 @@ def build_stream(n, src, dst, new_of_old, sort_in_row):
     shift = np.repeat(ptr2[:-1][has] - in_ptr[:-1][has], indeg[has])
     stream[np.arange(len(s_sorted)) + shift] = s_sorted
     return stream
+
+
+def blocked_stats(n, src, dst, new_of_old, blocks):
+    """Column blocking with virtual rows: (row, block) pairs that hold links, padding links."""
+    row = new_of_old[dst].astype(np.int64)
+    blk = new_of_old[src].astype(np.int64) * blocks // n
+    pairs = np.unique(row * blocks + blk)
+    indeg = np.bincount(row, minlength=n)
+    plain = int(np.maximum(indeg, 1).sum())
+    virtual = n * blocks
+    blocked = len(src) + (virtual - len(pairs))
+    return plain, blocked, virtual - len(pairs)
 
 
 def instr_matrix(stream, layout, n):
@@ -130,10 +145,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scale", type=float, default=0.25)
     ap.add_argument("--precision", default="fp64")
+    ap.add_argument("--spec", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--blocks", type=int, default=0, help="only price column blocking with this many blocks of x")
     args = ap.parse_args()
     import oracle as O
 
-    spec = dict(C2_SPEC)
+    spec = dict(C2_SPEC if args.spec == "c2" else C4_SPEC)
     for k in ("n_users", "n_items", "n_like", "n_friend"):
         spec[k] = max(4, int(spec[k] * args.scale))
     t0 = time.time()
@@ -143,6 +160,11 @@ def main():
     assert (np.diff(src) >= 0).all()
     print(f"graph: n={n} links={len(src)} ({time.time() - t0:.1f} s)", flush=True)
     new_of_old, n_hot, deg = relabel(n, src, dst)
+    if args.blocks:
+        plain, blocked, pads = blocked_stats(n, src, dst, new_of_old, args.blocks)
+        print(f"blocks={args.blocks}: stream {plain} links -> {blocked} links ({pads} padding links of empty (row, block) "
+              f"pairs, +{100.0 * (blocked - plain) / plain:.1f} %)")
+        return
     elt = 8 if args.precision == "fp64" else 4
     hub_bytes = (99 if elt == 8 else 163) * 1024 - 128
     hub = min((hub_bytes // elt) & ~3, n)
