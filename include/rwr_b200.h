@@ -102,7 +102,7 @@ typedef struct rwr_graph_info {
     int64_t device_bytes;    /* device memory held by the handle                                                */
     int32_t row_begin, row_end;  /* rows of W^T (internal labels) this rank iterates on: [0, N) unless partitioned   */
     int32_t n_ranks;         /* 1 unless the graph was created with rwr_*_create_partitioned                    */
-    int32_t reserved;
+    int32_t x_blocks;        /* 1; > 1 only with the experimental column blocking of x (RWR_X_BLOCKS probe knob)   */
 } rwr_graph_info;
 
 typedef struct rwr_run_info {

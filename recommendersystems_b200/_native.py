@@ -36,7 +36,7 @@ class rwr_graph_info(C.Structure):
                 ("hub_entries_fp64", C.c_int32), ("hub_entries_fp32", C.c_int32), ("n_chunks", C.c_int32),
                 ("max_in_degree", C.c_int32), ("max_out_degree", C.c_int32), ("build_ms", C.c_float),
                 ("synth_ms", C.c_float), ("device_bytes", C.c_int64), ("row_begin", C.c_int32), ("row_end", C.c_int32),
-                ("n_ranks", C.c_int32), ("reserved", C.c_int32)]
+                ("n_ranks", C.c_int32), ("x_blocks", C.c_int32)]
 
 
 class rwr_run_info(C.Structure):

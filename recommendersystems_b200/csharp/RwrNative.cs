@@ -34,7 +34,7 @@ namespace Recommenders.RWRBased.Native {
         public int n_dangling, layout, relabelled, n_hot, hub_entries_fp64, hub_entries_fp32, n_chunks, max_in_degree, max_out_degree;
         public float build_ms, synth_ms;
         public long device_bytes;
-        public int row_begin, row_end, n_ranks, reserved;
+        public int row_begin, row_end, n_ranks, x_blocks;
     }
 
     [StructLayout(LayoutKind.Sequential)]

@@ -706,6 +706,7 @@ int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info) {
     info->row_begin = g->row_begin;
     info->row_end = g->built ? g->row_end : 0;
     info->n_ranks = g->part_rows.empty() ? 1 : (int32_t)g->part_rows.size() - 1;
+    info->x_blocks = g->x_blocks;
     info->max_in_degree = (int32_t)g->max_in_degree;
     info->max_out_degree = (int32_t)g->max_out_degree;
     info->build_ms = g->build_ms;

@@ -70,6 +70,11 @@ struct rwr_graph {
     int32_t ws_tiles = 0;
     int32_t ws_tile_links = 0;          // links per tile of this graph's stream (WS_TILE, or WS_TILE_SMALL for small graphs)
     int64_t ws_nnz = 0;                 // nnz + one padding link per row without in-links
+    // column blocking of x (experimental, RWR_X_BLOCKS): the stream holds x_blocks streams back to back, block b with the
+    // links whose source label lies in [b * x_block_size, (b + 1) * x_block_size), over v_rows virtual rows each
+    int32_t x_blocks = 1;
+    int32_t x_block_size = 0;
+    int32_t v_rows = 0;                 // rows of this rank (= row_end - row_begin)
     DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
     DevBuf<u8> node_type_int;
     DevBuf<int32_t> items_by_id_desc;   // lazily: internal indices of ITEM nodes, id descending (full ranking)

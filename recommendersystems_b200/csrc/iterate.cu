@@ -140,7 +140,7 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool resid, d
 }
 
 struct RunWorkspace {
-    Scratch<unsigned char> xa, xb, ya;
+    Scratch<unsigned char> xa, xb, ya, yv;
     Scratch<double> carry, head, slot_S, slot_R;
     Scratch<IterCtl> ctl;
     void* x[2] = {nullptr, nullptr};      // the two gather vectors: scratch, or the peer-mapped buffers of a partitioned graph
@@ -148,6 +148,10 @@ struct RunWorkspace {
         if (g->p2p) { x[0] = g->px[0]; x[1] = g->px[1]; return; }
         xa.alloc(&g->scratch, vec_bytes); xb.alloc(&g->scratch, vec_bytes);
         x[0] = xa.p; x[1] = xb.p;
+    }
+    // column blocking of x (experimental): partial row sums of the virtual rows
+    void alloc_yv(rwr_graph* g, size_t elt) {
+        if (g->x_blocks > 1) yv.alloc(&g->scratch, (size_t)g->x_blocks * (size_t)g->v_rows * elt + 16);
     }
 };
 
@@ -186,6 +190,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot; p.debug = 0;
     p.head_partial = ws.head.p; p.carry = ws.carry.p;
     p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
+    p.yv = reinterpret_cast<T*>(ws.yv.p); p.x_blocks = g->x_blocks; p.v_rows = g->v_rows;
 
     // uniform constructor: S0 = sum over nodes of (dangling ? 1 : 1 - fl((1-c)*1))
     const double omc_d = (double)p.omc;
@@ -212,7 +217,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
         static const bool no_graph = getenv("RWR_NO_GRAPH") != nullptr;
         rwr_graph::IterGraph& ig = g->iter_graph[Prec<T>::id];
         const void* key[8] = {xa, xb, y_out, ws.ctl.p, ws.head.p, ws.carry.p, ws.slot_S.p, ws.slot_R.p};
-        const bool graphable = n_iter >= 2 && dist_n_ranks(g->comm) == 1 && !no_graph;
+        const bool graphable = n_iter >= 2 && dist_n_ranks(g->comm) == 1 && !no_graph && g->x_blocks == 1;
         const bool same = ig.n_iter == n_iter && ig.hub == hub && ig.c == c && memcmp(ig.ptr, key, sizeof(key)) == 0;
         if (graphable && same && (ig.exec || ig.seen)) {
             // second and later runs with this key: replay the graph of the whole loop (captured now if this is the second
@@ -295,7 +300,7 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
         Prec<T>::ybuf(res).alloc(std::max<size_t>(1, ld * (size_t)n_seeds), nullptr);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
+    ws.alloc_x(g, vec_bytes); ws.alloc_yv(g, sizeof(T)); ws.ya.alloc(&g->scratch, vec_bytes);
     ws.carry.alloc(&g->scratch, (size_t)g->ws_tiles + 1); ws.head.alloc(&g->scratch, (size_t)g->ws_tiles + 1);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, ((size_t)g->ws_tiles + 1) * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, ((size_t)g->ws_tiles + 1) * sizeof(double), st));
@@ -331,7 +336,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, vec_bytes);
+    ws.alloc_x(g, vec_bytes); ws.alloc_yv(g, sizeof(T)); ws.ya.alloc(&g->scratch, vec_bytes);
     ws.carry.alloc(&g->scratch, (size_t)g->ws_tiles + 1); ws.head.alloc(&g->scratch, (size_t)g->ws_tiles + 1);
     CUDA_CHECK(cudaMemsetAsync(ws.carry.p, 0, ((size_t)g->ws_tiles + 1) * sizeof(double), st));
     CUDA_CHECK(cudaMemsetAsync(ws.head.p, 0, ((size_t)g->ws_tiles + 1) * sizeof(double), st));
@@ -354,6 +359,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot;
     p.head_partial = ws.head.p; p.carry = ws.carry.p; p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
     p.r_prev = nullptr; p.y = ya;
+    p.yv = reinterpret_cast<T*>(ws.yv.p); p.x_blocks = g->x_blocks; p.v_rows = g->v_rows;
     { const char* dm = getenv("RWR_DEBUG_MODE"); p.debug = dm ? atoi(dm) : 0; }
     k_init<T><<<div_up(std::max((int)n, 1), 256), 256, 0, st>>>((int)n, seed_int, p.omc, p.inv, ya, xa, xb, ws.ctl.p, 0.0);
     KERNEL_CHECK();
@@ -394,7 +400,7 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     if (Prec<T>::id == RWR_FP32) ensure_fp32_arrays(g);
     RunWorkspace ws;
     const size_t vec_bytes = (n + 8) * sizeof(T);
-    ws.alloc_x(g, vec_bytes); ws.ya.alloc(&g->scratch, 16);
+    ws.alloc_x(g, vec_bytes); ws.alloc_yv(g, sizeof(T)); ws.ya.alloc(&g->scratch, 16);
     ws.carry.alloc(&g->scratch, (size_t)g->ws_tiles + 1); ws.head.alloc(&g->scratch, (size_t)g->ws_tiles + 1);
     const size_t slots = (size_t)g->sm_count * 8 + 8;
     ws.slot_S.alloc(&g->scratch, slots); ws.slot_R.alloc(&g->scratch, slots);

@@ -34,6 +34,11 @@ struct IterParams {
     double* slot_S;         // [blocks of k_finish_ws] restart-mass partials
     double* slot_R;
     IterCtl* ctl;
+    // column blocking of x (experimental): k_spmv_ws / k_cutrows_ws write the sums of the virtual rows b * v_rows + (row -
+    // row_begin) to yv (passed to them as `y`), k_finish_ws adds the x_blocks partial sums of a row in block order
+    T* yv;
+    int x_blocks;
+    int v_rows;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

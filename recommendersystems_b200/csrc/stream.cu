@@ -106,6 +106,68 @@ __global__ void k_ws_tiles(const u32* __restrict__ ptr2, int n, u32 q0, int row_
     ws_tile[t] = (u32)r | (q > ptr2[r] ? END_BIT : 0u);
 }
 
+// ---- column blocking of x with virtual rows (experimental) ----------------------------------
+// The links [lb, le) of the pull CSR are the rows [row_begin, row_end) of this rank.  Link p of row r whose source lies
+// in block b belongs to the virtual row b * R + (r - row_begin); keys / vals feed the stable sort by block that puts the
+// links into (block, row, accumulation order) order.
+__global__ void k_vrow_count(const u32* __restrict__ in_ptr, const int32_t* __restrict__ in_src, int row_begin, int row_end,
+                             u32 lb, u32 le, u32 block_size, int R, u32* __restrict__ cnt, u32* __restrict__ keys,
+                             u32* __restrict__ vals) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)(le - lb)) return;
+    const u32 p = lb + (u32)i;
+    int lo = row_begin, hi = row_end;            // in_ptr[lo] <= p < in_ptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+        if (in_ptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    const u32 b = (u32)in_src[p] / block_size;
+    atomicAdd(&cnt[(size_t)b * R + (size_t)(lo - row_begin)], 1u);
+    keys[i] = b;
+    vals[i] = (u32)i;
+}
+
+__global__ void k_vrow_len(const u32* __restrict__ cnt, size_t v, u32* __restrict__ len) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v) { const u32 c = cnt[i]; len[i] = c ? c : 1u; }
+}
+
+// like k_ws_fill, over the virtual rows: ptr2[v] = first stream position of virtual row v, cnt_ptr[v] = first entry of
+// `perm` (links in (block, row, accumulation) order, relative to lb) that belongs to it
+__global__ void k_ws_fill_blocked(const u32* __restrict__ ptr2, const u32* __restrict__ cnt_ptr, const u32* __restrict__ perm,
+                                  const int32_t* __restrict__ in_src, const double* __restrict__ in_val, int V, int n, u32 nnz2,
+                                  size_t padded, int32_t* __restrict__ ws_src, double* __restrict__ ws_val /* may be null */) {
+    const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phys >= padded) return;
+    const u32 o = (u32)(phys % WS_STAGE);
+    const u32 rnd = o / WS_STEP, ln = (o % WS_STEP) / 4, k = o % 4;
+    const size_t q = phys - o + (size_t)(ln * (WS_R * 4) + rnd * 4 + k);
+    if (q >= nnz2) {
+        ws_src[phys] = n;
+        if (ws_val) ws_val[phys] = 0.0;
+        return;
+    }
+    const int v = ws_row_of(ptr2, V, (u32)q);
+    const u32 j = (u32)q - ptr2[v];
+    const u32 b = cnt_ptr[v], cnt = cnt_ptr[v + 1] - b;
+    if (cnt == 0) {
+        ws_src[phys] = (int32_t)((u32)n | END_BIT);
+        if (ws_val) ws_val[phys] = 0.0;
+    } else {
+        const u32 link = perm[b + j];
+        ws_src[phys] = (int32_t)((u32)in_src[link] | (j == cnt - 1 ? END_BIT : 0u));
+        if (ws_val) ws_val[phys] = in_val[link];
+    }
+}
+
+// RWR_X_BLOCKS=<B> (2..64): probe knob, off by default
+static int x_blocks_wanted() {
+    const char* e = getenv("RWR_X_BLOCKS");
+    if (!e) return 1;
+    const int v = atoi(e);
+    return (v >= 2 && v <= 64) ? v : 1;
+}
+
 void stream_prepare(rwr_graph* g) {
     cudaStream_t st = g->stream;
     const int n = g->n;
@@ -144,6 +206,57 @@ void stream_prepare(rwr_graph* g) {
         q0 = lim[0];
         nnz2 = lim[1] - lim[0];
     }
+    // column blocking (experimental): the stream is rebuilt over x_blocks * (row_end - row_begin) virtual rows
+    DevBuf<u32> ptr2v, cnt_ptr, perm, perm_alt;
+    const u32* perm_sorted = nullptr;
+    u32 link_base = 0;
+    g->x_blocks = 1;
+    g->v_rows = g->row_end - g->row_begin;
+    g->x_block_size = n;
+    {
+        const int want = x_blocks_wanted();
+        const int R = g->v_rows;
+        if (want > 1 && R > 0) {
+            const u32 block_size = (u32)((((size_t)n + want - 1) / want + 15) & ~(size_t)15);
+            const int xb = (int)(((size_t)n + block_size - 1) / block_size);
+            if (xb > 1) {
+                const u64 V64 = (u64)xb * (u64)R;
+                if (V64 >= (1ull << 31)) RWR_FAIL(RWR_E_UNSUPPORTED, "%d blocks of %d rows exceed 2^31 virtual rows", xb, R);
+                const size_t V = (size_t)V64;
+                u32 lim[2] = {0, 0};
+                CUDA_CHECK(cudaMemcpyAsync(&lim[0], g->in_ptr.p + g->row_begin, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(&lim[1], g->in_ptr.p + g->row_end, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                const u32 lb = lim[0], le = lim[1];
+                const size_t er = (size_t)(le - lb);
+                if ((u64)er + V64 + WS_TILE >= (1ull << 32)) RWR_FAIL(RWR_E_UNSUPPORTED, "blocked edge stream exceeds 32-bit offsets");
+                DevBuf<u32> keys, keys_alt, total_v;
+                cnt_ptr.alloc(V + 1); ptr2v.alloc(V + 1); total_v.alloc(1);
+                keys.alloc(er); keys_alt.alloc(er); perm.alloc(er); perm_alt.alloc(er);
+                CUDA_CHECK(cudaMemsetAsync(cnt_ptr.p, 0, (V + 1) * sizeof(u32), st));
+                if (er) {
+                    k_vrow_count<<<div_up(er, 256), 256, 0, st>>>(g->in_ptr.p, g->in_src.p, g->row_begin, g->row_end, lb, le, block_size,
+                                                                 R, cnt_ptr.p, keys.p, perm.p);
+                    KERNEL_CHECK();
+                }
+                k_vrow_len<<<div_up(V, 256), 256, 0, st>>>(cnt_ptr.p, V, ptr2v.p);
+                KERNEL_CHECK();
+                prim::exclusive_scan<u32>(ptr2v.p, ptr2v.p, V, total_v.p, st, &g->pool);
+                CUDA_CHECK(cudaMemcpyAsync(&nnz2, total_v.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaMemcpyAsync(ptr2v.p + V, total_v.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+                prim::exclusive_scan<u32>(cnt_ptr.p, cnt_ptr.p, V, total_v.p, st, &g->pool);
+                CUDA_CHECK(cudaMemcpyAsync(cnt_ptr.p + V, total_v.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+                const bool fl = prim::radix_sort<u32>(keys.p, keys_alt.p, perm.p, perm_alt.p, er, ceil_log2_u64((u64)xb), st, &g->pool);
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                perm_sorted = fl ? perm_alt.p : perm.p;
+                link_base = lb;
+                q0 = 0;
+                g->x_blocks = xb;
+                g->x_block_size = (int32_t)block_size;
+            }
+        }
+    }
+    const bool blocked = g->x_blocks > 1;
     // tile size: WS_TILE links, but smaller graphs (the reference's ego networks) get smaller tiles so that their links
     // still spread over every warp of every SM (big_x_probe.py with RWR_TILE_LINKS: 3.9 M links 39 / 42 / 59 us per
     // iteration with 512 / 1024 / 4096-link tiles, 19.8 M links 92 / 84 / 96 us, 61 M links 244 / 214 / 208 us)
@@ -161,10 +274,19 @@ void stream_prepare(rwr_graph* g) {
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     if (valued) g->ws_val64.alloc(padded, &g->pool);
     g->ws_tile.alloc((size_t)n_tiles + 1, &g->pool);
-    if (padded)
-        k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, q0,
-                                                      nnz2, padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
-    k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, (u32)tile_links, g->ws_tile.p);
+    if (blocked) {
+        const int V = g->x_blocks * g->v_rows;
+        if (padded)
+            k_ws_fill_blocked<<<div_up(padded, 256), 256, 0, st>>>(ptr2v.p, cnt_ptr.p, perm_sorted, g->in_src.p + link_base,
+                                                                  valued ? g->in_val64.p + link_base : nullptr, V, n, nnz2, padded,
+                                                                  g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+        k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2v.p, V, 0u, V, n_tiles, (u32)tile_links, g->ws_tile.p);
+    } else {
+        if (padded)
+            k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, q0,
+                                                          nnz2, padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+        k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, (u32)tile_links, g->ws_tile.p);
+    }
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (parts > 1) {          // the whole-graph pull arrays are only needed by the batched path, which a slice does not run
@@ -494,7 +616,8 @@ __global__ void __launch_bounds__(FIX_THREADS) k_cutrows_ws(const IterParams<T> 
 //   y_t (+ S for the seed row, + S/N everywhere for the uniform restart), next x_t = fl(fl((1-c) y_t) * inv_t),
 //   restart mass and L1 residual partials; the last block adds the partials in a fixed order -> next S, residual,
 //   iteration count, convergence flag (Model.cs:57-66, :110-115).
-template <typename T, bool RESID>
+// BLOCKED (column blocking of x, experimental): the raw sum of a row is the sum of its x_blocks virtual rows, block order.
+template <typename T, bool RESID, bool BLOCKED>
 __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p, double thr, int use_thr) {
     __shared__ double scratch[2 * FIN_THREADS / 32];
     __shared__ int is_last;
@@ -506,10 +629,18 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
     const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
     double accS = 0.0, accR = 0.0;
     for (int row = p.row_begin + blockIdx.x * FIN_THREADS + threadIdx.x; row < p.row_end; row += gridDim.x * FIN_THREADS) {
-        T y = ld_stream(p.y + row, pol_first);
+        T y;
+        if (BLOCKED) {
+            const T* part = p.yv + (row - p.row_begin);
+            y = ld_stream(part, pol_first);
+            for (int b = 1; b < p.x_blocks; b++) y = add_rn(y, ld_stream(part + (size_t)b * (size_t)p.v_rows, pol_first));
+        } else {
+            y = ld_stream(p.y + row, pol_first);
+        }
         const T invr = ld_stream(p.inv + row, pol_first);
         if (row == seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
         if (seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
+        if (BLOCKED) p.y[row] = y;
         const T rw = mul_rn(p.omc, y);
         // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
         const T xn = mul_rn(rw, invr);
@@ -578,14 +709,29 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     // maximum (a per-launch value would race between threads whose graphs have different hub sizes); the carve-out a
     // launch gets still follows the dynamic size it asks for
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem_optin));
-    kern<<<ws_main_grid(g), threads, smem, g->stream>>>(p);
+    if (p.x_blocks > 1) {                         // the row sums of the virtual rows go to yv
+        IterParams<T> pv = p;
+        pv.y = p.yv;
+        kern<<<ws_main_grid(g), threads, smem, g->stream>>>(pv);
+    } else {
+        kern<<<ws_main_grid(g), threads, smem, g->stream>>>(p);
+    }
     KERNEL_CHECK();
 }
 template <typename T>
 void ws_launch_finish_only(rwr_graph* g, const IterParams<T>& p, bool resid, double thr, int use_thr) {
+    if (p.x_blocks > 1) {
+        IterParams<T> pv = p;
+        pv.y = p.yv;
+        k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(pv);
+        if (resid) k_finish_ws<T, true, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+        else k_finish_ws<T, false, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+        KERNEL_CHECK();
+        return;
+    }
     k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(p);
-    if (resid) k_finish_ws<T, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
-    else k_finish_ws<T, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    if (resid) k_finish_ws<T, true, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    else k_finish_ws<T, false, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
     KERNEL_CHECK();
 }
 template <typename T>
