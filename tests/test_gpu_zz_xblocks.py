@@ -1,6 +1,7 @@
-"""Experimental column blocking of x (RWR_X_BLOCKS): written when no GPU time was left in round 1,
-so it is off by default and this test may fail without failing the suite.  It runs last (file name) and in a process of
-its own (tests/xblocks_worker.py), with a time limit, so that nothing it does can disturb the other GPU tests."""
+"""Experimental column blocking of x (RWR_X_BLOCKS), off by default.  Written at the very end of
+round 1: one GPU run with 4 blocks passed (profiles/microbench/xblocks_parity_r01.log); other block counts have not run
+yet and may fail without failing the suite.  The check runs last (file name) and in a process of its own
+(tests/xblocks_worker.py: the knob is read from the environment when a graph is built), with a time limit."""
 import os
 import subprocess
 import sys
@@ -12,8 +13,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.xfail(strict=False, reason="experimental path, not yet validated on a GPU (off by default)")
-@pytest.mark.parametrize("blocks", [4, 7])
+@pytest.mark.parametrize("blocks", [4, pytest.param(7, marks=pytest.mark.xfail(
+    strict=False, reason="experimental path: this block count has not run on a GPU yet"))])
 def test_column_blocking_matches_the_oracle(blocks):
     r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "xblocks_worker.py"), str(blocks)], cwd=ROOT,
                        capture_output=True, text=True, timeout=600)
