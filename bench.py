@@ -368,7 +368,7 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
                         f"over NVLink (CUDA IPC), 16-byte ncclAllReduce per iteration",
             "n_nodes": info.n_nodes, "nnz": info.nnz,
             "gteps": round(info.nnz * N_ITER * steps / (it_ms * 1e-3) / 1e9, 2), "ms_per_iteration": round(per_iter_ms, 4),
-            "rows_rank0": [info.row_begin, info.row_end],
+            "rows_rank0": [info.row_begin, info.row_end], "x_blocks": info.x_blocks,
             "allgather_bytes_per_rank_per_iteration": int(gathered),
             "hbm": {"algorithmic_bytes_per_gpu_per_iteration": int(alg), "achieved": round(alg / (per_iter_ms * 1e-3) / 1e9, 1),
                     "peak": peak, "unit": "GB/s", "frac": round(alg / (per_iter_ms * 1e-3) / 1e9 / peak, 4)},
