@@ -1,9 +1,10 @@
 // spmm.cu -- K8: batched power iteration  Y[N,B] = (1-c) W^T R[N,B] + S[B] o Q  for B seed columns at once.
 //
-// Same restatement of Model.cs:76-108 as iterate.cu, with one rank vector per seed laid out row-major: a gathered
+// Same restatement of Model.cs:76-108 as stream.cu, with one rank vector per seed laid out row-major: a gathered
 // source row is 64 contiguous bytes (B = 8 FP64 / 16 FP32 columns), so one matrix pass serves B seeds and every
 // gathered sector is fully used.  Four lanes (a quad) own one destination row at a time, 16 bytes of the row each.
-//   k_spmm        8 groups x 128 threads per CTA, merge-path tiles as in k_spmv; tile indices (and values) staged in
+//   k_spmm        8 groups x 128 threads per CTA, merge-path tiles over the pull CSR (k_partition, iterate.cu: equal
+//                 rows + links per tile); tile indices (and values) staged in
 //                 shared memory; rows < 32 nnz: one quad, sources in storage order; 32..255: one warp; >= 256: the group
 //   k_spmm_fixup  rows cut by a tile boundary, the B seed entries (+S_j), fixed-order reduction of the restart masses
 #include <algorithm>
