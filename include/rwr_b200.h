@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RWR_ABI_VERSION 1
+#define RWR_ABI_VERSION 2
 
 typedef enum rwr_status {
     RWR_OK = 0,
@@ -70,6 +70,15 @@ typedef struct rwr_opts {
                            /* `edges` but leave the matrix, as the methodology switches of Experiment.cs:84-101 do   */
                            /* by retyping FRIENDSHIP links (mask 1 << RWR_EDGE_FRIENDSHIP); LIKE links masked here   */
                            /* still exclude their targets from the recommendation (Recommender.cs:20-24)             */
+    int32_t zero_weight_type_mask; /* bit t set: links of EdgeType t stay in the matrix with weight 0.0 -- what               */
+                           /* DataLoader.addMentionCount2 produces for MENTION links when the member has no FRIENDSHIP link  */
+                           /* (`nFriendhips * Math.Log(..) / ..`, DataLoader.cs:423-434; Methodology 15)                     */
+    int32_t x_blocks;      /* column blocking of the gather vector for graphs whose x is far beyond L2: 0 = auto, 1 = off,    */
+                           /* 2..64 = that many blocks                                                       */
+    int32_t empty_seed_ok; /* 1: a seed without raw links is accepted by the recommendation calls -- an `edges` entry that   */
+                           /* exists but is empty (Recommender.cs:21 only throws for a MISSING key; the flattened input      */
+                           /* cannot tell the two apart, the managed shim checks ContainsKey itself and sets this)           */
+    int32_t reserved;      /* must be 0                                                                                       */
 } rwr_opts;
 
 /* Deterministic synthetic generator (this repository's spec; replaces TweetRecommender/DataLoader.cs:256-436
@@ -102,7 +111,7 @@ typedef struct rwr_graph_info {
     int64_t device_bytes;    /* device memory held by the handle                                                */
     int32_t row_begin, row_end;  /* rows of W^T (internal labels) this rank iterates on: [0, N) unless partitioned   */
     int32_t n_ranks;         /* 1 unless the graph was created with rwr_*_create_partitioned                    */
-    int32_t x_blocks;        /* 1; > 1 only with the experimental column blocking of x (RWR_X_BLOCKS probe knob)   */
+    int32_t x_blocks;        /* column blocks of the gather vector the edge stream was built with (1 = none)       */
 } rwr_graph_info;
 
 typedef struct rwr_run_info {
@@ -139,7 +148,11 @@ int rwr_graph_export_links(rwr_graph* g, int64_t* node_id, int32_t* node_type, i
                            int32_t* etype, double* w);
 /* `Graph.graph` (Graph.cs:43): row_ptr[N+1], col[nnz], val[nnz]; null rows have equal row_ptr entries      */
 int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val);
+/* `graph[i][k].type` (Graph.cs:73-74 copies the whole ForwardLink): the EdgeType of every explicit link, CSR order     */
+int rwr_graph_get_csr_types(rwr_graph* g, int32_t* etype /*[nnz]*/);
 int rwr_graph_get_degrees(rwr_graph* g, int32_t* out_degree /*N explicit links*/, int32_t* raw_degree /*N, may be NULL*/);
+/* On a handle created with rwr_*_create_partitioned this is a collective call (every rank destroys its handle; the
+ * peer-mapped gather vectors are unmapped by all ranks before any rank frees them), made before rwr_comm_destroy.   */
 void rwr_graph_destroy(rwr_graph* g);
 
 /* ---- model: `new Model(graph, c, seed)` + `run(int)` Model.cs:33-50, :68-73 ----
@@ -182,6 +195,39 @@ int rwr_profile_iteration(rwr_graph* g, int32_t seed, double c, int32_t precisio
 /* ---- evaluation (next row N1): Experiment.cs:121-128 on a ranking held on the host ---- */
 int rwr_evaluate(const int64_t* ranked_ids, int64_t n, const int64_t* test_ids, int64_t n_test, int32_t* hits,
                  double* avg_precision);
+
+/* ---- N3: `Methodology` -> feature set (TweetRecommender/DataLoader.cs:142-219, Experiment.cs:7-16, :84-101) as link-type
+ * masks.  A graph that carries every relation (what Methodology.ALL loads) becomes methodology m's graph by leaving the
+ * link types of *undefined_type_mask out of the matrix (types DataLoader would not have loaded, plus FRIENDSHIP where it
+ * is only "temporarily included" and retyped UNDEFINED at Experiment.cs:84-101) and by zeroing the weight of the types in
+ * *zero_weight_type_mask (MENTION for methodology 15, whose mention weights are `0 * ln(cnt) / ..`: no friendship was
+ * loaded).  *feature_mask: bit f = Feature f (FRIENDSHIP, FOLLOWSHIP_ON_THIRDPARTY, AUTHORSHIP, MENTIONCOUNT) is in the
+ * list graphConfiguration(List<Feature>, fold) receives.  Pass the two masks in rwr_opts.  Node count and third-party
+ * nodes stay those of the full graph (the reference would not have created ETC nodes without followship: its scores are
+ * the same up to the common factor N'/N, Model.cs:44).  Returns RWR_E_INVALID outside 0..15.                            */
+int rwr_methodology_masks(int32_t methodology, int32_t* feature_mask, int32_t* undefined_type_mask,
+                          int32_t* zero_weight_type_mask);
+
+/* ---- N2: k-fold hold-out on the device: DataLoader.splitLikeHistory (DataLoader.cs:122-140) and the LIKE links that
+ * never enter the graph for the test fold (:287-298), for any number of test users at once.  Call between create and
+ * rwr_graph_build.  For each (distinct) user u: likes(u) = targets of u's raw LIKE links that are ITEM nodes, ordered by
+ * node id (`likesList.Sort()`); unit = |likes| / n_folds; test fold = positions [unit*fold, fold < n_folds-1 ?
+ * unit*(fold+1) : |likes|).  The links u->t and t->u of type LIKE with t in the test fold leave `edges`.  The test sets
+ * stay in the handle (rwr_evaluate_users) and are returned: test_ptr[n_users+1], test_ids[min(total, cap)] (node ids,
+ * ascending per user), *n_test = total.  Output pointers may be NULL.  The reference holds out the ego user (index 0)
+ * only; BASELINE config 5 holds out 100k users of one graph (n_folds = 10, fold = 9: the newest tenth).                */
+int rwr_graph_hold_out(rwr_graph* g, const int32_t* users, int32_t n_users, int32_t n_folds, int32_t fold,
+                       int64_t* test_ptr, int64_t* test_ids, int64_t cap, int64_t* n_test);
+
+/* ---- N1: Experiment.cs:121-128 for many users without materialising the rankings: `Recommendation(u, c, n_iter)` in
+ * seed tiles; the position of every test item in the (score desc, id desc) order of Recommender.cs:34-38 is counted on
+ * the device (1 + number of candidates that rank before it), then hits[u] = nHits, avg_precision[u] = (nHits == 0) ? 0 :
+ * sumPrecision / nHits with sumPrecision accumulated in ranking order (Experiment.cs:124-127, :136), hits_at_k[u] = test
+ * items among the first k.  A test id that is no candidate (unknown id, not an ITEM, or one of u's LIKE targets) is no
+ * hit.  test_ptr / test_ids NULL: the sets stored by rwr_graph_hold_out, `users` NULL: its user list.                  */
+int rwr_evaluate_users(rwr_graph* g, const int32_t* users, int32_t n_users, const int64_t* test_ptr, const int64_t* test_ids,
+                       double c, int32_t n_iter, int32_t precision, int32_t k, int32_t* hits, double* avg_precision,
+                       int32_t* hits_at_k, int32_t* n_test_of_user, rwr_run_info* info /* may be NULL */);
 
 /* ---- row-partitioned single graph (no reference analogue): slices of W^T + NCCL allGather per iteration ----
  * One process per GPU.  Rank 0 calls rwr_comm_unique_id and hands the 128 bytes to the other ranks by any means

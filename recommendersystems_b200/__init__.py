@@ -5,9 +5,10 @@ NodeType, EdgeType) on top of the C ABI of librwr_b200.so (include/rwr_b200.h). 
 extension must be built (`python -c "import __graft_entry__ as g; g.build()"`) and a CUDA device must be present
 for anything that computes.
 """
-from .rwr import (Comm, EdgeType, ForwardLink, Graph, Model, Node, NodeType, Recommender, RwrError, SynthSpec,
-                  FP32, FP64, evaluate, widen_float)
+from .rwr import (Comm, EdgeType, Feature, ForwardLink, Graph, Methodology, Model, Node, NodeType, Recommender, RwrError,
+                  SynthSpec, FP32, FP64, evaluate, evaluate_users, methodology_masks, methodology_options, widen_float)
 from . import _native
 
-__all__ = ["Comm", "EdgeType", "ForwardLink", "Graph", "Model", "Node", "NodeType", "Recommender", "RwrError", "SynthSpec",
-           "FP32", "FP64", "evaluate", "widen_float", "_native"]
+__all__ = ["Comm", "EdgeType", "Feature", "ForwardLink", "Graph", "Methodology", "Model", "Node", "NodeType", "Recommender",
+           "RwrError", "SynthSpec", "FP32", "FP64", "evaluate", "evaluate_users", "methodology_masks", "methodology_options",
+           "widen_float", "_native"]

@@ -10,6 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "librwr_b200.so")
 
+ABI_VERSION = 2
 RWR_OK = 0
 RWR_E_INVALID, RWR_E_BADSEED, RWR_E_ALREADY_BUILT, RWR_E_BADINDEX, RWR_E_NOT_BUILT = -1, -2, -3, -4, -5
 RWR_E_CUDA, RWR_E_NCCL, RWR_E_OOM, RWR_E_UNSUPPORTED = -6, -7, -8, -9
@@ -20,7 +21,8 @@ LAYOUT_AUTO, LAYOUT_VALUED, LAYOUT_INDEX = 0, 1, 2
 class rwr_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("layout", C.c_int32), ("relabel", C.c_int32), ("hub_entries", C.c_int32),
                 ("batch_width", C.c_int32), ("kernel", C.c_int32), ("stream", C.c_uint64),
-                ("hot_min_degree", C.c_int32), ("undefined_type_mask", C.c_int32)]
+                ("hot_min_degree", C.c_int32), ("undefined_type_mask", C.c_int32), ("zero_weight_type_mask", C.c_int32),
+                ("x_blocks", C.c_int32), ("empty_seed_ok", C.c_int32), ("reserved", C.c_int32)]
 
 
 class rwr_synth_spec(C.Structure):
@@ -58,6 +60,7 @@ SYMBOLS = {
     "rwr_graph_get_info": (C.c_int, [_vp, C.POINTER(rwr_graph_info)]),
     "rwr_graph_export_links": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rwr_graph_get_csr": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "rwr_graph_get_csr_types": (C.c_int, [_vp, _vp]),
     "rwr_graph_get_degrees": (C.c_int, [_vp, _vp, _vp]),
     "rwr_graph_destroy": (None, [_vp]),
     "rwr_run_fixed": (C.c_int, [_vp, _vp, _i32, _f64, _i32, _i32, _pp]),
@@ -71,6 +74,10 @@ SYMBOLS = {
     "rwr_recommend": (C.c_int, [_vp, _vp, _i32, _f64, _i32, _i32, _i32, _vp, _vp, _vp, C.POINTER(rwr_run_info)]),
     "rwr_profile_iteration": (C.c_int, [_vp, _i32, _f64, _i32, _i32, _vp, _vp]),
     "rwr_evaluate": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp]),
+    "rwr_methodology_masks": (C.c_int, [_i32, _vp, _vp, _vp]),
+    "rwr_graph_hold_out": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _i64, _vp]),
+    "rwr_evaluate_users": (C.c_int, [_vp, _vp, _i32, _vp, _vp, _f64, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     C.POINTER(rwr_run_info)]),
     "rwr_comm_unique_id": (C.c_int, [_vp]),
     "rwr_comm_create": (C.c_int, [_i32, _i32, _vp, C.POINTER(rwr_opts), _pp]),
     "rwr_comm_destroy": (None, [_vp]),
@@ -94,7 +101,7 @@ def lib() -> C.CDLL:
             fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
-        if L.rwr_abi_version() != 1:
+        if L.rwr_abi_version() != ABI_VERSION:
             raise ImportError("librwr_b200.so ABI version mismatch")
         _lib = L
     return _lib

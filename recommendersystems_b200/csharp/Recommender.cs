@@ -16,6 +16,8 @@ namespace Recommenders.RWRBased {
         // Full ranking: every ITEM node the user has not liked, (score desc, id desc).
         public List<KeyValuePair<long, double>> Recommendation(int idxTargetUser, float dampingFactor, int nIteration) {
             double c = dampingFactor;
+            graph.RequireBuilt();
+            graph.RequireEdgesEntry(idxTargetUser);
             ResultHandle res;
             RwrNative.Check(RwrNative.rwr_run_fixed(graph.handle, new[] { idxTargetUser }, 1, c, nIteration, RwrNative.FP64, out res));
             using (res) {
@@ -36,6 +38,8 @@ namespace Recommenders.RWRBased {
                 return (topN > 0 && topN < all.Count) ? all.GetRange(0, topN) : all;
             }
             double c = dampingFactor;
+            graph.RequireBuilt();
+            graph.RequireEdgesEntry(idxTargetUser);
             var ids = new long[topN]; var scores = new double[topN]; var counts = new int[1];
             RwrRunInfo info;
             RwrNative.Check(RwrNative.rwr_recommend(graph.handle, new[] { idxTargetUser }, 1, c, nIteration, RwrNative.FP64, topN, ids,
@@ -48,6 +52,8 @@ namespace Recommenders.RWRBased {
         // Not in the reference: n seeds at once through the SpMM tiles (Experiment-style evaluation of many users).
         public List<KeyValuePair<long, double>>[] RecommendationBatch(int[] users, float dampingFactor, int nIteration, int topN) {
             double c = dampingFactor;
+            graph.RequireBuilt();
+            foreach (int u in users) graph.RequireEdgesEntry(u);
             var ids = new long[users.Length * topN]; var scores = new double[users.Length * topN]; var counts = new int[users.Length];
             RwrRunInfo info;
             RwrNative.Check(RwrNative.rwr_recommend(graph.handle, users, users.Length, c, nIteration, RwrNative.FP64, topN, ids, scores,

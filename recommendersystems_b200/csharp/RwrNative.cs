@@ -15,8 +15,10 @@ namespace Recommenders.RWRBased.Native {
     public struct RwrOpts {
         public int device, layout, relabel, hub_entries, batch_width, kernel;
         public ulong stream;
-        public int hot_min_degree, undefined_type_mask;
-        public static RwrOpts Default() { return new RwrOpts { device = -1, hub_entries = -1 }; }
+        public int hot_min_degree, undefined_type_mask, zero_weight_type_mask, x_blocks, empty_seed_ok, reserved;
+        // empty_seed_ok: the managed Graph checks `edges.ContainsKey(seed)` itself (KeyNotFoundException, Recommender.cs:21),
+        // so a key that exists with an empty list is served like the reference serves it
+        public static RwrOpts Default() { return new RwrOpts { device = -1, hub_entries = -1, empty_seed_ok = 1 }; }
     }
 
     [StructLayout(LayoutKind.Sequential)]
@@ -72,6 +74,7 @@ namespace Recommenders.RWRBased.Native {
         [DllImport(Lib)] public static extern int rwr_graph_export_links(GraphHandle g, long[] nodeId, int[] nodeType, int[] src,
             int[] dst, int[] etype, double[] w);
         [DllImport(Lib)] public static extern int rwr_graph_get_csr(GraphHandle g, long[] rowPtr, int[] col, double[] val);
+        [DllImport(Lib)] public static extern int rwr_graph_get_csr_types(GraphHandle g, int[] etype);
         [DllImport(Lib)] public static extern int rwr_graph_get_degrees(GraphHandle g, int[] outDegree, int[] rawDegree);
         [DllImport(Lib)] public static extern void rwr_graph_destroy(IntPtr g);
 
@@ -91,6 +94,15 @@ namespace Recommenders.RWRBased.Native {
             int precision, int k, long[] outIds, double[] outScores, int[] outCounts, out RwrRunInfo info);
         [DllImport(Lib)] public static extern int rwr_evaluate(long[] rankedIds, long n, long[] testIds, long nTest, out int hits,
             out double avgPrecision);
+        // callers of the hot path: Methodology masks (DataLoader.cs:142-219), k-fold hold-out (DataLoader.cs:122-140),
+        // hits / average precision of many users (Experiment.cs:121-128)
+        [DllImport(Lib)] public static extern int rwr_methodology_masks(int methodology, out int featureMask, out int undefinedTypeMask,
+            out int zeroWeightTypeMask);
+        [DllImport(Lib)] public static extern int rwr_graph_hold_out(GraphHandle g, int[] users, int nUsers, int nFolds, int fold,
+            long[] testPtr, long[] testIds, long cap, out long nTest);
+        [DllImport(Lib)] public static extern int rwr_evaluate_users(GraphHandle g, int[] users, int nUsers, long[] testPtr, long[] testIds,
+            double c, int nIter, int precision, int k, int[] hits, double[] avgPrecision, int[] hitsAtK, int[] nTestOfUser,
+            out RwrRunInfo info);
         [DllImport(Lib)] public static extern int rwr_profile_iteration(GraphHandle g, int seed, double c, int precision, int reps,
             out float spmvMs, out float fixupMs);
 

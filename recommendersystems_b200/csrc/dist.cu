@@ -80,6 +80,7 @@ NcclApi& nccl() {
 struct rwr_comm {
     int rank = 0, n_ranks = 1, device = 0;
     ncclComm_t comm = nullptr;
+    bool fake = false;      // RWR_FAKE_COMM probe: a slice of a partitioned graph on one GPU, no exchange (timing only)
 };
 
 int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
@@ -89,7 +90,7 @@ __global__ void k_dist_noop() {}
 
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
     rwr_comm* c = g->comm;
-    if (!c || c->n_ranks < 2) return;
+    if (!c || c->n_ranks < 2 || c->fake) return;
     NcclApi& api = nccl();
     NCCL_CHECK(api.GroupStart());
     for (int r = 0; r < c->n_ranks; r++) {
@@ -103,7 +104,7 @@ void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
 
 void dist_exchange(rwr_graph* g, void* x_next, size_t elt, double* two_doubles) {
     rwr_comm* c = g->comm;
-    if (!c || c->n_ranks < 2) return;
+    if (!c || c->n_ranks < 2 || c->fake) return;
     if (x_next) dist_allgather_rows(g, x_next, elt);
     NCCL_CHECK(nccl().AllReduce(two_doubles, two_doubles, 2, ncclFloat64, ncclSum, c->comm, g->stream));
 }
@@ -115,7 +116,7 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // syn
 void dist_setup_p2p(rwr_graph* g) {
     rwr_comm* c = g->comm;
     g->p2p = false;
-    if (!c || c->n_ranks < 2 || c->n_ranks > 8 || getenv("RWR_DIST_NO_P2P")) return;
+    if (!c || c->n_ranks < 2 || c->n_ranks > 8 || c->fake || getenv("RWR_DIST_NO_P2P")) return;
     cudaStream_t st = g->stream;
     const int P = c->n_ranks;
     const size_t bytes = ((size_t)g->n + 8) * 8;
@@ -169,14 +170,27 @@ void dist_setup_p2p(rwr_graph* g) {
     g->p2p = true;
 }
 
+// Teardown in three steps (collective on a partitioned handle): every rank closes its mappings of the peers' buffers,
+// all ranks meet on the communicator, and only then does each rank free the buffers it exported -- cudaFree of memory a
+// peer still has open through cudaIpcOpenMemHandle is undefined behaviour.
 void dist_release_p2p(rwr_graph* g) {
+    if (!g->px[0] && !g->px[1] && g->peer_px[0].empty() && g->peer_px[1].empty()) { g->p2p = false; return; }
     const int me = dist_rank(g->comm);
     for (int b = 0; b < 2; b++) {
         for (int r = 0; r < (int)g->peer_px[b].size(); r++)
             if (r != me && g->peer_px[b][r]) cudaIpcCloseMemHandle(g->peer_px[b][r]);
         g->peer_px[b].clear();
-        if (g->px[b]) { cudaFree(g->px[b]); g->pool.bytes -= (int64_t)(((size_t)g->n + 8) * 8); g->px[b] = nullptr; }
     }
+    rwr_comm* c = g->comm;
+    if (c && c->n_ranks > 1 && !c->fake && c->comm && g_nccl.lib && g->px[0]) {
+        // px[0] doubles as the 8-byte payload of the barrier: nobody reads it any more
+        if (g_nccl.AllReduce(g->px[0], g->px[0], 1, ncclFloat64, ncclSum, c->comm, g->stream) == ncclSuccess)
+            cudaStreamSynchronize(g->stream);
+        else
+            cudaGetLastError();
+    }
+    for (int b = 0; b < 2; b++)
+        if (g->px[b]) { cudaFree(g->px[b]); g->pool.bytes -= (int64_t)(((size_t)g->n + 8) * 8); g->px[b] = nullptr; }
     g->p2p = false;
 }
 
@@ -205,9 +219,14 @@ int rwr_comm_create(int32_t rank, int32_t n_ranks, const void* id128, const rwr_
         c->n_ranks = n_ranks;
         if (opts && opts->device >= 0) CUDA_CHECK(cudaSetDevice(opts->device));
         CUDA_CHECK(cudaGetDevice(&c->device));
-        ncclUniqueId id;
-        memcpy(&id, id128, sizeof(id));
-        NCCL_CHECK(nccl().CommInitRank(&c->comm, n_ranks, id, rank));
+        // probe knob: one slice of a partitioned graph on a single GPU, no NCCL and no exchange --
+        // kernel timing and ncu captures of a slice only, the results of a run are wrong
+        c->fake = getenv("RWR_FAKE_COMM") != nullptr;
+        if (!c->fake) {
+            ncclUniqueId id;
+            memcpy(&id, id128, sizeof(id));
+            NCCL_CHECK(nccl().CommInitRank(&c->comm, n_ranks, id, rank));
+        }
         *out = c;
         return RWR_OK;
     } catch (const RwrError& e) {

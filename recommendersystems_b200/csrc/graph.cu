@@ -60,7 +60,7 @@ __global__ void k_lower_bounds(const KeyT* __restrict__ keys, size_t e, int32_t 
 // K1: flag explicit links (type != UNDEFINED) and validate their targets (IndexOutOfRange at Model.cs:87)
 // `mask`: bit t set = links of EdgeType t count as UNDEFINED (the methodology switches of Experiment.cs:84-101, which
 // retype FRIENDSHIP links to UNDEFINED before buildGraph(), as one option instead of a rewrite of the link list)
-__device__ __forceinline__ bool link_is_explicit(u8 t, u32 mask) { return t != RWR_EDGE_UNDEFINED && !((mask >> (t & 31)) & 1u); }
+__device__ __forceinline__ bool link_is_explicit(u8 t, u32 mask) { return t != RWR_EDGE_UNDEFINED && !(t < 32 && ((mask >> t) & 1u)); }
 
 __global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __restrict__ dst, size_t e0, int32_t n,
                                  u32 mask, u32* __restrict__ flags, int* bad) {
@@ -76,16 +76,26 @@ __global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __r
 }
 
 // K3: stable compaction of the explicit links (insertion order kept: pos is an exclusive scan of the flags)
+// `zero_mask`: links of these types keep their slot with weight 0.0 (rwr_opts.zero_weight_type_mask)
 __global__ void k_compact(const u8* __restrict__ type, const u32* __restrict__ pos, const int32_t* __restrict__ src,
-                          const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0, u32 mask,
+                          const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0, u32 mask, u32 zero_mask,
                           int32_t* __restrict__ src_of, int32_t* __restrict__ col, double* __restrict__ wv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < e0 && link_is_explicit(type[i], mask)) {
+    if (i < e0) {
+        const u8 t = type[i];
+        if (!link_is_explicit(t, mask)) return;
         u32 p = pos[i];
         src_of[p] = src[i];
         col[p] = dst[i];
-        wv[p] = w[i];
+        wv[p] = (t < 32 && ((zero_mask >> t) & 1u)) ? 0.0 : w[i];
     }
+}
+
+// `graph[i][k].type`: the types of the explicit links in CSR order
+__global__ void k_compact_types(const u8* __restrict__ type, const u32* __restrict__ pos, size_t e0, u32 mask,
+                                int32_t* __restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e0 && link_is_explicit(type[i], mask)) out[pos[i]] = (int32_t)type[i];
 }
 
 __global__ void k_row_ptr_from_pos(const u32* __restrict__ raw_ptr, const u32* __restrict__ pos, size_t e0, u32 nnz,
@@ -388,6 +398,13 @@ void graph_finish_create(rwr_graph* g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+void graph_rebuild_raw_ptr(rwr_graph* g) {
+    g->raw_ptr.alloc((size_t)g->n + 1, &g->pool);
+    k_lower_bounds<int32_t><<<grid_for((size_t)g->n + 1), 256, 0, g->stream>>>(g->raw_src.p, (size_t)g->e0, g->n, g->raw_ptr.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+}
+
 static void graph_build_impl(rwr_graph* g) {
     if (g->built) RWR_FAIL(RWR_E_ALREADY_BUILT, "buildGraph() called twice (ArgumentException at Graph.cs:86)");
     CUDA_CHECK(cudaSetDevice(g->device));
@@ -432,7 +449,7 @@ static void graph_build_impl(rwr_graph* g) {
     // ---- K3: stable scatter (skipped when no UNDEFINED link exists: the raw arrays already are the CSR)
     DevBuf<double> wv_own;
     const double* wv;
-    if (nnz == e0) {
+    if (nnz == e0 && g->opts.zero_weight_type_mask == 0) {
         g->compacted = false;
         g->row_ptr = g->raw_ptr.p;
         g->col = g->raw_dst.p;
@@ -445,7 +462,8 @@ static void graph_build_impl(rwr_graph* g) {
         g->src_of_own.alloc(nnz, &g->pool);
         wv_own.alloc(nnz);
         k_compact<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, g->raw_src.p, g->raw_dst.p, g->raw_w.p, e0,
-                                                (u32)g->opts.undefined_type_mask, g->src_of_own.p, g->col_own.p, wv_own.p);
+                                                (u32)g->opts.undefined_type_mask, (u32)g->opts.zero_weight_type_mask,
+                                                g->src_of_own.p, g->col_own.p, wv_own.p);
         k_row_ptr_from_pos<<<grid_for((size_t)n + 1), 256, 0, st>>>(g->raw_ptr.p, pos.p, e0, (u32)nnz, n, g->row_ptr_own.p);
         KERNEL_CHECK();
         g->row_ptr = g->row_ptr_own.p;
@@ -556,6 +574,7 @@ static void graph_build_impl(rwr_graph* g) {
             KERNEL_CHECK();
             CUDA_CHECK(cudaStreamSynchronize(st));
             g->part_rows.assign(plan.start, plan.start + parts + 1);
+            g->part_hot.assign(plan.hot_of, plan.hot_of + parts);
         }
     }
 
@@ -563,7 +582,7 @@ static void graph_build_impl(rwr_graph* g) {
     g->in_ptr.alloc((size_t)n + 1, &g->pool);
     g->in_src.alloc(nnz + IDX_PAD, &g->pool);
     CUDA_CHECK(cudaMemsetAsync(g->in_src.p, 0, (nnz + IDX_PAD) * sizeof(int32_t), st));
-    if (layout == RWR_LAYOUT_VALUED) g->in_val64.alloc(nnz, &g->pool);
+    if (layout == RWR_LAYOUT_VALUED) g->in_val64.alloc(nnz + IDX_PAD, &g->pool);   // k_spmm reads whole groups of 4
     {
         DevBuf<u32> k0, k1, v0, v1;
         k0.alloc(nnz); k1.alloc(nnz); v0.alloc(nnz); v1.alloc(nnz);
@@ -760,6 +779,30 @@ int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val)
         CUDA_CHECK(cudaStreamSynchronize(st));
         for (size_t i = 0; i <= n; i++) row_ptr[i] = (int64_t)rp[i];
     }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    return RWR_OK;
+    RWR_API_END
+}
+
+int rwr_graph_get_csr_types(rwr_graph* g, int32_t* etype) {
+    RWR_API_BEGIN
+    if (!g || !etype) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    CUDA_CHECK(cudaSetDevice(g->device));
+    cudaStream_t st = g->stream;
+    AllocStream alloc_on(st);
+    const size_t e0 = (size_t)g->e0, nnz = (size_t)g->nnz;
+    if (nnz == 0) return RWR_OK;
+    DevBuf<u32> pos;
+    DevBuf<int> bad;
+    DevBuf<int32_t> out;
+    pos.alloc(e0); bad.alloc(1); out.alloc(nnz);
+    k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, g->n, (u32)g->opts.undefined_type_mask, pos.p, bad.p);
+    KERNEL_CHECK();
+    prim::exclusive_scan<u32>(pos.p, pos.p, e0, nullptr, st, &g->pool);
+    k_compact_types<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, e0, (u32)g->opts.undefined_type_mask, out.p);
+    KERNEL_CHECK();
+    CUDA_CHECK(cudaMemcpyAsync(etype, out.p, nnz * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     return RWR_OK;
     RWR_API_END

@@ -80,10 +80,22 @@ struct rwr_graph {
     DevBuf<int32_t> items_by_id_desc;   // lazily: internal indices of ITEM nodes, id descending (full ranking)
     int32_t n_items = 0;
 
+    // ---- hold-out state (N2, experiment.cu): test users (original labels) and their held-out tweet ids
+    std::vector<int32_t> held_users;
+    std::vector<int64_t> held_ptr;      // [held_users + 1]
+    std::vector<int64_t> held_ids;      // node ids, ascending per user
+    // ---- node id -> internal label lookup for the evaluation (N1, select.cu): ids in unsigned order, lazily built
+    DevBuf<u64> ids_sorted;
+    DevBuf<u32> label_of_sorted;
+
     // ---- row-partitioned mode
     rwr_comm* comm = nullptr;
     int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
     std::vector<int> part_rows;           // [n_ranks + 1] first row of every rank's slice
+    std::vector<int> part_hot;            // [n_ranks] hot (degree-sorted, dealt one by one) nodes at the head of every slice
+    // hub table of a partitioned graph: the part_hub_seg hottest labels of every slice, slice after slice; the edge stream
+    // stores hub sources as their table slot and every other source as label + part_hub (stream.cu: HubMap)
+    int32_t part_hub = 0, part_hub_seg = 0;
     // gather vectors of a partitioned graph live in two persistent buffers that every peer maps through CUDA IPC: the
     // epilogue kernel stores a rank's slice of the next x straight into the peers' copies over NVLink (dist.cu)
     bool p2p = false;

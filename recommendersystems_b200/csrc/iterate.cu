@@ -155,6 +155,14 @@ struct RunWorkspace {
     }
 };
 
+// rows below this label are hot (their x entries are stored evict-last by the epilogue): the degree-sorted label prefix,
+// or -- on a slice of a partitioned graph, whose labels are dealt over the slices -- the hot head of this rank's own rows
+static int hot_limit(const rwr_graph* g) {
+    const int parts = dist_n_ranks(g->comm);
+    if (parts > 1 && (int)g->part_hot.size() == parts) return g->row_begin + g->part_hot[dist_rank(g->comm)];
+    return g->n_hot;
+}
+
 // peers' copies of the buffer `x_next` is (row-partitioned graphs with peer-mapped gather vectors)
 template <typename T>
 static void set_peers(rwr_graph* g, IterParams<T>& p, const void* x_next) {
@@ -187,7 +195,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
     p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles; p.tile_links = g->ws_tile_links;
     p.row_begin = g->row_begin; p.row_end = g->row_end;
     p.omc = (T)(1.0 - c);                                      // Model.cs:84 `(1 - dampingFactor)`
-    p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot; p.debug = 0;
+    p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = hot_limit(g); p.debug = 0;
     p.head_partial = ws.head.p; p.carry = ws.carry.p;
     p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
     p.yv = reinterpret_cast<T*>(ws.yv.p); p.x_blocks = g->x_blocks; p.v_rows = g->v_rows;
@@ -356,7 +364,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     p.n = g->n; p.inv = Prec<T>::inv(g);
     p.ws_src = g->ws_src.p; p.ws_val = Prec<T>::wsval(g); p.ws_tile = g->ws_tile.p; p.ws_tiles = g->ws_tiles; p.tile_links = g->ws_tile_links;
     p.row_begin = g->row_begin; p.row_end = g->row_end;
-    p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = g->n_hot;
+    p.omc = (T)(1.0 - c); p.seed = seed_int; p.inv_n = n ? 1.0 / (double)n : 0.0; p.hub = hub; p.n_hot = hot_limit(g);
     p.head_partial = ws.head.p; p.carry = ws.carry.p; p.slot_S = ws.slot_S.p; p.slot_R = ws.slot_R.p; p.ctl = ws.ctl.p;
     p.r_prev = nullptr; p.y = ya;
     p.yv = reinterpret_cast<T*>(ws.yv.p); p.x_blocks = g->x_blocks; p.v_rows = g->v_rows;

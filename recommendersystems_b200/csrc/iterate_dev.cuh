@@ -18,7 +18,12 @@ struct IterParams {
     int parted;             // row-partitioned: the epilogue leaves its partial sums in ctl->red for the allReduce
     int n_peers;            // peers whose copy of x_next the epilogue writes directly (NVLink peer stores)
     void* peer_next[7];
-    const T* x;             // gather source, internal labels
+    const T* x;             // gather source, internal labels (k_spmv_ws of a partitioned graph: shifted down by `hub` entries,
+                            // the stream stores non-hub sources as label + hub)
+    const T* xhub;          // k_spmv_ws: the unshifted gather vector the hub table is loaded from
+    int hub_segs;           // > 0: partitioned graph, the hub table is hub_segs segments of hub_seg_len entries, segment s
+    int hub_seg_len;        //      starting at label hub_start[s] (the hottest labels of every rank's slice)
+    int hub_start[8];
     const T* inv;
     const T* r_prev;        // previous rank (residual)
     T* y;

@@ -383,12 +383,13 @@ static void seed_raw_range(rwr_graph* g, int seed, u32* begin, u32* end) {
 }
 
 static void mark_excluded(rwr_graph* g, int seed, u32* excl, size_t words) {
+    if (seed == -1) RWR_FAIL(RWR_E_INVALID, "a uniform-restart Model (seed -1) has no target user: Recommendation() needs one (Recommender.cs:14)");
     if (seed < 0 || seed >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
     u32 b, e;
     seed_raw_range(g, seed, &b, &e);
-    if (b == e) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
+    if (b == e && !g->opts.empty_seed_ok) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
     CUDA_CHECK(cudaMemsetAsync(excl, 0, words * sizeof(u32), g->stream));
-    k_mark_excluded<<<div_up(e - b, 256), 256, 0, g->stream>>>(g->raw_dst.p, g->raw_type.p, b, e, g->new_of_old.p, g->n, excl);
+    if (e > b) k_mark_excluded<<<div_up(e - b, 256), 256, 0, g->stream>>>(g->raw_dst.p, g->raw_type.p, b, e, g->new_of_old.p, g->n, excl);
     KERNEL_CHECK();
     g->pool.launches += 1;
 }
@@ -670,7 +671,7 @@ static void recommend_tiles(rwr_graph* g, const int32_t* seeds, int n_seeds, dou
         CUDA_CHECK(cudaEventRecord(e2, st));
         CUDA_CHECK(cudaEventSynchronize(e2));
         for (int j = 0; j < cnt; j++) {
-            if (h_cnt[TILE_MAXB + j])
+            if (h_cnt[TILE_MAXB + j] && !g->opts.empty_seed_ok)
                 RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seeds[s0 + j]);
             if (h_cnt[j] > TILE_CAND_CAP) {              // too many candidates at the bound (ties): exact per-column path
                 topk_one<T>(g, y.p + j, B, seeds[s0 + j], k, excl.p, words, block_out.p, grid, d_ids.p + (size_t)(s0 + j) * k,
@@ -708,19 +709,19 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
     if (n_iter < 0) n_iter = 0;
     CUDA_CHECK(cudaSetDevice(g->device));
     AllocStream alloc_on(g->stream);
-    bool all_regular = true;
     for (int s = 0; s < n_seeds; s++) {
-        if (seeds[s] < -1 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);
-        if (seeds[s] < 0) all_regular = false;
+        // Recommendation(idxTargetUser, ..) always has a target user; the uniform constructor (seed -1) is a Model-only path
+        if (seeds[s] == -1) RWR_FAIL(RWR_E_INVALID, "seed -1 (uniform restart) is not a target user: use rwr_run_fixed + rwr_scores");
+        if (seeds[s] < 0 || seeds[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d outside [0, %d)", seeds[s], g->n);
     }
     // a row slice of a partitioned graph has no whole-graph pull CSR: seeds run one at a time through the edge stream
-    if (k <= TOPK_MAX && all_regular && (n_seeds < 2 || g->opts.batch_width == 1 || g->comm)) {
+    if (k <= TOPK_MAX && (n_seeds < 2 || g->opts.batch_width == 1 || g->comm)) {
         if (precision == RWR_FP64) recommend_singles<double>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
         else recommend_singles<float>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
         return RWR_OK;
     }
-    if (k > TOPK_MAX || !all_regular) {
-        // result-object path per seed (k > 16 needs the full ranking; seed -1 is the uniform constructor)
+    if (k > TOPK_MAX) {
+        // result-object path per seed (k > 16 needs the full ranking)
         for (int s = 0; s < n_seeds; s++) {
             rwr_result* res = nullptr;
             int rc = rwr_run_fixed(g, seeds + s, 1, c, n_iter, precision, &res);
@@ -738,6 +739,280 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
     }
     if (precision == RWR_FP64) recommend_tiles<double>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
     else recommend_tiles<float>(g, seeds, n_seeds, c, n_iter, k, out_ids, out_scores, out_counts, info);
+    return RWR_OK;
+    RWR_API_END
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ N1: evaluation on the device
+// Experiment.cs:121-128 walks the full ranking and, for every test item it meets, adds nHits / (i + 1).  The ranking is a
+// total order (score desc, id desc: Recommender.cs:34-38), so the position of a test item is 1 + the number of candidates
+// that rank before it -- a count, no sort.  One pass over the rank tile Y[n, B] serves all B users of the tile.
+constexpr int EV_GROUP = 8;                      // test items a thread counts for per pass over Y
+
+struct EvalItem {
+    u64 key;        // score key of the test item (0 with idx < 0: not a candidate)
+    int64_t id;
+    int idx;        // internal label, -1: the id is not a candidate of this user
+    u32 before;     // candidates ranking before it
+};
+
+// unsigned-order image of a node id
+__device__ __forceinline__ u64 id_key(int64_t id) { return (u64)id ^ 0x8000000000000000ULL; }
+
+__global__ void k_ev_id_keys(const int64_t* __restrict__ id_int, int n, u64* __restrict__ keys, u32* __restrict__ vals) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) { keys[j] = id_key(id_int[j]); vals[j] = (u32)j; }
+}
+
+// items of the tile: column `col` owns items [iptr[col], iptr[col + 1]); resolve id -> label, candidate test, score key
+template <typename T>
+__global__ void k_ev_resolve(const int64_t* __restrict__ test_ids, const int* __restrict__ iptr, int cols, int B,
+                             const u64* __restrict__ ids_sorted, const u32* __restrict__ label_of_sorted, int n,
+                             const u8* __restrict__ type_int, const u32* __restrict__ excl, size_t words,
+                             const T* __restrict__ y, EvalItem* __restrict__ items) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= iptr[cols]) return;
+    int col = 0;
+    while (col + 1 < cols && iptr[col + 1] <= i) col++;
+    const int64_t id = test_ids[i];
+    const u64 k = id_key(id);
+    int lo = 0, hi = n;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ids_sorted[mid] < k) lo = mid + 1; else hi = mid; }
+    EvalItem it;
+    it.key = 0; it.id = id; it.idx = -1; it.before = 0;
+    if (lo < n && ids_sorted[lo] == k) {
+        const int j = (int)label_of_sorted[lo];
+        const u32* ex = excl + (size_t)col * words;
+        if (type_int[j] == RWR_NODE_ITEM && !((ex[j >> 5] >> (j & 31)) & 1u)) {
+            it.idx = j;
+            it.key = score_key((double)y[(size_t)j * B + col]);
+        }
+    }
+    items[i] = it;
+}
+
+// thread (row lane, column): counts, for up to EV_GROUP items of its column, the candidates of its rows that rank before
+template <typename T, int B>
+__global__ void __launch_bounds__(TOPK_THREADS) k_ev_count(const T* __restrict__ y, const u8* __restrict__ type_int,
+                                                           const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
+                                                           size_t words, int n, int cols, const int* __restrict__ iptr, int pass,
+                                                           EvalItem* __restrict__ items) {
+    const int col = threadIdx.x % B, rlane = threadIdx.x / B;
+    constexpr int RPB = TOPK_THREADS / B;
+    if (col >= cols) return;
+    const int first = iptr[col] + pass * EV_GROUP;
+    const int cnt = min(EV_GROUP, iptr[col + 1] - first);
+    if (cnt <= 0) return;
+    u64 tk[EV_GROUP];
+    int64_t tid[EV_GROUP];
+    u32 c[EV_GROUP];
+#pragma unroll
+    for (int g = 0; g < EV_GROUP; g++) {
+        const bool on = g < cnt && items[first + (g < cnt ? g : 0)].idx >= 0;
+        tk[g] = on ? items[first + g].key : ~0ULL;        // nothing ranks before an inactive slot
+        tid[g] = on ? items[first + g].id : INT64_MAX;
+        c[g] = 0;
+    }
+    const u32* ex = excl + (size_t)col * words;
+    for (int j = blockIdx.x * RPB + rlane; j < n; j += gridDim.x * RPB) {
+        if (type_int[j] != RWR_NODE_ITEM) continue;
+        if ((ex[j >> 5] >> (j & 31)) & 1u) continue;
+        const u64 key = score_key((double)y[(size_t)j * B + col]);
+        const int64_t id = id_int[j];
+#pragma unroll
+        for (int g = 0; g < EV_GROUP; g++) c[g] += (key > tk[g]) || (key == tk[g] && id > tid[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < EV_GROUP; g++)
+        if (g < cnt && c[g]) atomicAdd(&items[first + g].before, c[g]);
+}
+
+// one block per column: positions in ascending order (rank counting), then the reference's loop (Experiment.cs:121-128)
+__global__ void __launch_bounds__(TOPK_THREADS) k_ev_finish(const EvalItem* __restrict__ items, const int* __restrict__ iptr, int k,
+                                                            u32* __restrict__ sorted_pos /* scratch, [items] */,
+                                                            int* __restrict__ hits, double* __restrict__ ap, int* __restrict__ hits_at_k) {
+    const int col = blockIdx.x;
+    const int b = iptr[col], e = iptr[col + 1];
+    __shared__ int n_valid;
+    if (threadIdx.x == 0) n_valid = 0;
+    __syncthreads();
+    for (int i = b + threadIdx.x; i < e; i += TOPK_THREADS) {
+        if (items[i].idx < 0) continue;
+        const u32 pos = items[i].before;
+        int r = 0;
+        for (int j = b; j < e; j++) r += (items[j].idx >= 0) && (items[j].before < pos || (items[j].before == pos && j < i));
+        sorted_pos[b + r] = pos;
+        atomicAdd(&n_valid, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int nHits = 0, atk = 0;
+        double sumPrecision = 0.0;
+        for (int r = 0; r < n_valid; r++) {
+            const u32 i0 = sorted_pos[b + r];                      // zero-based index in the recommendation list
+            nHits += 1;
+            sumPrecision += (double)nHits / (double)(i0 + 1);       // Experiment.cs:126
+            if ((int)i0 < k) atk++;
+        }
+        hits[col] = nHits;
+        ap[col] = nHits == 0 ? 0.0 : sumPrecision / nHits;          // Experiment.cs:136
+        hits_at_k[col] = atk;
+    }
+}
+
+static void ensure_id_lookup(rwr_graph* g) {
+    if (g->ids_sorted.p) return;
+    cudaStream_t st = g->stream;
+    const int n = g->n;
+    DevBuf<u64> k0, k1;
+    DevBuf<u32> v0, v1;
+    k0.alloc(n); k1.alloc(n); v0.alloc(n); v1.alloc(n);
+    if (n) k_ev_id_keys<<<div_up(n, 256), 256, 0, st>>>(g->node_id_int.p, n, k0.p, v0.p);
+    KERNEL_CHECK();
+    const bool fl = prim::radix_sort<u64>(k0.p, k1.p, v0.p, v1.p, n, 64, st, &g->pool);
+    g->ids_sorted.alloc(n, &g->pool);
+    g->label_of_sorted.alloc(n, &g->pool);
+    if (n) {
+        CUDA_CHECK(cudaMemcpyAsync(g->ids_sorted.p, fl ? k1.p : k0.p, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+        CUDA_CHECK(cudaMemcpyAsync(g->label_of_sorted.p, fl ? v1.p : v0.p, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+template <typename T>
+static void evaluate_tiles(rwr_graph* g, const int32_t* users, int n_users, const int64_t* test_ptr, const int64_t* test_ids,
+                           double c, int n_iter, int k, int32_t* hits, double* avg_precision, int32_t* hits_at_k,
+                           rwr_run_info* info) {
+    cudaStream_t st = g->stream;
+    const int B = spmm_tile_width(sizeof(T) == 4 ? RWR_FP32 : RWR_FP64);
+    const size_t n = (size_t)g->n;
+    if (sizeof(T) == 4) ensure_fp32_arrays(g);
+    ensure_id_lookup(g);
+    std::vector<int32_t> n2o((size_t)n_users);
+    Scratch<int32_t> d_users;
+    d_users.alloc(&g->scratch, n_users);
+    {
+        Scratch<int32_t> d_int;
+        d_int.alloc(&g->scratch, n_users);
+        CUDA_CHECK(cudaMemcpyAsync(d_users.p, users, (size_t)n_users * 4, cudaMemcpyHostToDevice, st));
+        k_lookup<<<div_up((size_t)n_users, 256), 256, 0, st>>>(g->new_of_old.p, d_users.p, n_users, d_int.p);
+        KERNEL_CHECK();
+        CUDA_CHECK(cudaMemcpyAsync(n2o.data(), d_int.p, (size_t)n_users * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
+    const int64_t total_items = test_ptr[n_users];
+    Scratch<int64_t> d_test;
+    d_test.alloc(&g->scratch, (size_t)std::max<int64_t>(total_items, 1));
+    if (total_items) CUDA_CHECK(cudaMemcpyAsync(d_test.p, test_ids, (size_t)total_items * 8, cudaMemcpyHostToDevice, st));
+    int64_t max_tile_items = 1;
+    for (int s0 = 0; s0 < n_users; s0 += B)
+        max_tile_items = std::max(max_tile_items, test_ptr[std::min(n_users, s0 + B)] - test_ptr[s0]);
+    Scratch<T> y;
+    y.alloc(&g->scratch, n * B + 16);
+    const size_t words = (n + 31) / 32 + 1;
+    const int grid = std::max(1, std::min(std::min(g->sm_count * 4, TOPK_MAX_GRID), (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
+    Scratch<u32> excl_t, sorted_pos;
+    Scratch<EvalItem> items;
+    Scratch<int> d_iptr, no_links, d_hits, d_atk;
+    Scratch<double> d_ap;
+    excl_t.alloc(&g->scratch, (size_t)B * words);
+    items.alloc(&g->scratch, (size_t)max_tile_items); sorted_pos.alloc(&g->scratch, (size_t)max_tile_items);
+    d_iptr.alloc(&g->scratch, TILE_MAXB + 1); no_links.alloc(&g->scratch, TILE_MAXB);
+    d_hits.alloc(&g->scratch, n_users); d_atk.alloc(&g->scratch, n_users); d_ap.alloc(&g->scratch, n_users);
+    DevEvent e0, e1, e2;
+    int64_t launches = 0;
+    float it_ms = 0.f, tot_ms = 0.f;
+    for (int s0 = 0; s0 < n_users; s0 += B) {
+        const int cnt = std::min(B, n_users - s0);
+        CUDA_CHECK(cudaEventRecord(e0, st));
+        spmm_run_tile<T>(g, n2o.data() + s0, cnt, c, n_iter, y.p, &launches);
+        CUDA_CHECK(cudaEventRecord(e1, st));
+        int h_iptr[TILE_MAXB + 1];
+        int max_items = 0;
+        for (int j = 0; j <= TILE_MAXB; j++) h_iptr[j] = (int)(test_ptr[s0 + std::min(j, cnt)] - test_ptr[s0]);
+        for (int j = 0; j < cnt; j++) max_items = std::max(max_items, h_iptr[j + 1] - h_iptr[j]);
+        const int tile_items = h_iptr[cnt];
+        CUDA_CHECK(cudaMemcpyAsync(d_iptr.p, h_iptr, sizeof(h_iptr), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(excl_t.p, 0, (size_t)B * words * sizeof(u32), st));
+        CUDA_CHECK(cudaMemsetAsync(no_links.p, 0, TILE_MAXB * sizeof(int), st));
+        k_mark_excluded_tile<<<dim3(8, cnt), 256, 0, st>>>(g->raw_dst.p, g->raw_type.p, g->raw_ptr.p, d_users.p + s0, g->new_of_old.p,
+                                                          g->n, words, excl_t.p, no_links.p);
+        if (tile_items) {
+            k_ev_resolve<T><<<div_up((size_t)tile_items, 256), 256, 0, st>>>(d_test.p + test_ptr[s0], d_iptr.p, cnt, B, g->ids_sorted.p,
+                                                                            g->label_of_sorted.p, g->n, g->node_type_int.p, excl_t.p,
+                                                                            words, y.p, items.p);
+            for (int pass = 0; pass * EV_GROUP < max_items; pass++) {
+                if (B == 8)
+                    k_ev_count<T, 8><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
+                                                                   d_iptr.p, pass, items.p);
+                else
+                    k_ev_count<T, 16><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
+                                                                    d_iptr.p, pass, items.p);
+                launches++;
+            }
+        }
+        k_ev_finish<<<cnt, TOPK_THREADS, 0, st>>>(items.p, d_iptr.p, k, sorted_pos.p, d_hits.p + s0, d_ap.p + s0, d_atk.p + s0);
+        KERNEL_CHECK();
+        launches += 3;
+        int h_no[TILE_MAXB];
+        CUDA_CHECK(cudaMemcpyAsync(h_no, no_links.p, sizeof(h_no), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaEventRecord(e2, st));
+        CUDA_CHECK(cudaEventSynchronize(e2));
+        for (int j = 0; j < cnt; j++)
+            if (h_no[j] && !g->opts.empty_seed_ok) RWR_FAIL(RWR_E_BADSEED, "user %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", users[s0 + j]);
+        float a = 0.f, b = 0.f;
+        CUDA_CHECK(cudaEventElapsedTime(&a, e0, e1));
+        CUDA_CHECK(cudaEventElapsedTime(&b, e0, e2));
+        it_ms += a; tot_ms += b;
+    }
+    CUDA_CHECK(cudaMemcpyAsync(hits, d_hits.p, (size_t)n_users * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(hits_at_k, d_atk.p, (size_t)n_users * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(avg_precision, d_ap.p, (size_t)n_users * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+    if (info) {
+        info->n_seeds = n_users; info->n_nodes = g->n; info->precision = sizeof(T) == 4 ? RWR_FP32 : RWR_FP64;
+        info->iterations = n_iter; info->residual = NAN; info->iterate_ms = it_ms; info->total_ms = tot_ms;
+        info->kernel_launches = launches;
+    }
+}
+
+extern "C" {
+
+int rwr_evaluate_users(rwr_graph* g, const int32_t* users, int32_t n_users, const int64_t* test_ptr, const int64_t* test_ids,
+                       double c, int32_t n_iter, int32_t precision, int32_t k, int32_t* hits, double* avg_precision,
+                       int32_t* hits_at_k, int32_t* n_test_of_user, rwr_run_info* info) {
+    RWR_API_BEGIN
+    if (!g || !hits || !avg_precision || !hits_at_k) RWR_FAIL(RWR_E_INVALID, "NULL argument");
+    if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    if (g->comm) RWR_FAIL(RWR_E_UNSUPPORTED, "evaluation runs on seed tiles: use a replicated graph and shard the users over the ranks");
+    if (precision != RWR_FP64 && precision != RWR_FP32) RWR_FAIL(RWR_E_INVALID, "unknown precision %d", precision);
+    if (info) memset(info, 0, sizeof(*info));
+    if (!users) {                                   // the users and test sets rwr_graph_hold_out stored
+        if (test_ptr || test_ids) RWR_FAIL(RWR_E_INVALID, "test sets without a user list");
+        if (n_users != (int32_t)g->held_users.size()) RWR_FAIL(RWR_E_INVALID, "n_users %d != %zu held-out users", n_users, g->held_users.size());
+        users = g->held_users.data();
+    }
+    if (!test_ptr) {
+        if (n_users != (int32_t)g->held_users.size() || !std::equal(users, users + n_users, g->held_users.begin()))
+            RWR_FAIL(RWR_E_INVALID, "no test sets given and the user list is not the one of rwr_graph_hold_out");
+        test_ptr = g->held_ptr.data();
+        test_ids = g->held_ids.data();
+    }
+    if (n_users < 0 || (n_users && test_ptr[n_users] && !test_ids)) RWR_FAIL(RWR_E_INVALID, "bad test sets");
+    for (int s = 0; s < n_users; s++) {
+        if (users[s] < 0 || users[s] >= g->n) RWR_FAIL(RWR_E_BADSEED, "user %d outside [0, %d)", users[s], g->n);
+        if (test_ptr[s + 1] < test_ptr[s]) RWR_FAIL(RWR_E_INVALID, "test_ptr is not ascending");
+        if (n_test_of_user) n_test_of_user[s] = (int32_t)(test_ptr[s + 1] - test_ptr[s]);
+    }
+    if (n_users == 0) return RWR_OK;
+    if (n_iter < 0) n_iter = 0;
+    if (k < 0) k = 0;
+    CUDA_CHECK(cudaSetDevice(g->device));
+    AllocStream alloc_on(g->stream);
+    if (precision == RWR_FP64) evaluate_tiles<double>(g, users, n_users, test_ptr, test_ids, c, n_iter, k, hits, avg_precision, hits_at_k, info);
+    else evaluate_tiles<float>(g, users, n_users, test_ptr, test_ids, c, n_iter, k, hits, avg_precision, hits_at_k, info);
     return RWR_OK;
     RWR_API_END
 }

@@ -68,9 +68,27 @@ __device__ __forceinline__ int ws_row_of(const u32* __restrict__ ptr2, int n, u3
     return lo;
 }
 
+// Hub table of a partitioned graph.  The label order is dealt over the slices (graph.cu: k_deal_labels), so the hottest
+// sources are the first labels of EVERY slice, not one label prefix.  The stream therefore stores a source as
+//   slot = s * seg_len + (label - start[s])   when it is one of the seg_len hottest labels of slice s   (slot < H)
+//   label + H                                 otherwise (k_spmv_ws gets the gather vector shifted down by H entries)
+// and k_spmv_ws keeps its one-compare, one-load gather.  H == 0: labels are stored as they are.
+struct HubMap {
+    int parts, seg_len, H;
+    int start[8];
+};
+__device__ __forceinline__ u32 hub_translate(const HubMap& m, u32 label) {
+    if (m.H == 0) return label;
+    for (int s = 0; s < m.parts; s++) {
+        const u32 j = label - (u32)m.start[s];
+        if (j < (u32)m.seg_len) return (u32)(s * m.seg_len) + j;
+    }
+    return label + (u32)m.H;
+}
+
 // The stream covers the links [q0, q0 + nnz2) of the whole-graph numbering (q0 > 0 for a row slice of a partitioned graph).
 __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ in_ptr, const int32_t* __restrict__ in_src,
-                          const double* __restrict__ in_val, int n, u32 q0, u32 nnz2, size_t padded,
+                          const double* __restrict__ in_val, int n, u32 q0, u32 nnz2, size_t padded, const HubMap hm,
                           int32_t* __restrict__ ws_src, double* __restrict__ ws_val /* may be null */) {
     const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (phys >= padded) return;
@@ -79,8 +97,9 @@ __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ 
     const u32 o = (u32)(phys % WS_STAGE);
     const u32 rnd = o / WS_STEP, ln = (o % WS_STEP) / 4, k = o % 4;
     const size_t q = phys - o + (size_t)(ln * (WS_R * 4) + rnd * 4 + k);
+    const u32 zero_entry = (u32)n + (u32)hm.H;   // x[n] == 0
     if (q >= nnz2) {                          // tail padding of the last tile: zero entry, no flag
-        ws_src[phys] = n;
+        ws_src[phys] = (int32_t)zero_entry;
         if (ws_val) ws_val[phys] = 0.0;
         return;
     }
@@ -88,10 +107,10 @@ __global__ void k_ws_fill(const u32* __restrict__ ptr2, const u32* __restrict__ 
     const u32 j = q0 + (u32)q - ptr2[r];
     const u32 b = in_ptr[r], deg = in_ptr[r + 1] - b;
     if (deg == 0) {
-        ws_src[phys] = (int32_t)((u32)n | END_BIT);
+        ws_src[phys] = (int32_t)(zero_entry | END_BIT);
         if (ws_val) ws_val[phys] = 0.0;
     } else {
-        ws_src[phys] = (int32_t)((u32)in_src[b + j] | (j == deg - 1 ? END_BIT : 0u));
+        ws_src[phys] = (int32_t)(hub_translate(hm, (u32)in_src[b + j]) | (j == deg - 1 ? END_BIT : 0u));
         if (ws_val) ws_val[phys] = in_val[b + j];
     }
 }
@@ -136,14 +155,16 @@ __global__ void k_vrow_len(const u32* __restrict__ cnt, size_t v, u32* __restric
 // `perm` (links in (block, row, accumulation) order, relative to lb) that belongs to it
 __global__ void k_ws_fill_blocked(const u32* __restrict__ ptr2, const u32* __restrict__ cnt_ptr, const u32* __restrict__ perm,
                                   const int32_t* __restrict__ in_src, const double* __restrict__ in_val, int V, int n, u32 nnz2,
-                                  size_t padded, int32_t* __restrict__ ws_src, double* __restrict__ ws_val /* may be null */) {
+                                  size_t padded, const HubMap hm, int32_t* __restrict__ ws_src,
+                                  double* __restrict__ ws_val /* may be null */) {
     const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (phys >= padded) return;
     const u32 o = (u32)(phys % WS_STAGE);
     const u32 rnd = o / WS_STEP, ln = (o % WS_STEP) / 4, k = o % 4;
     const size_t q = phys - o + (size_t)(ln * (WS_R * 4) + rnd * 4 + k);
+    const u32 zero_entry = (u32)n + (u32)hm.H;
     if (q >= nnz2) {
-        ws_src[phys] = n;
+        ws_src[phys] = (int32_t)zero_entry;
         if (ws_val) ws_val[phys] = 0.0;
         return;
     }
@@ -151,20 +172,21 @@ __global__ void k_ws_fill_blocked(const u32* __restrict__ ptr2, const u32* __res
     const u32 j = (u32)q - ptr2[v];
     const u32 b = cnt_ptr[v], cnt = cnt_ptr[v + 1] - b;
     if (cnt == 0) {
-        ws_src[phys] = (int32_t)((u32)n | END_BIT);
+        ws_src[phys] = (int32_t)(zero_entry | END_BIT);
         if (ws_val) ws_val[phys] = 0.0;
     } else {
         const u32 link = perm[b + j];
-        ws_src[phys] = (int32_t)((u32)in_src[link] | (j == cnt - 1 ? END_BIT : 0u));
+        ws_src[phys] = (int32_t)(hub_translate(hm, (u32)in_src[link]) | (j == cnt - 1 ? END_BIT : 0u));
         if (ws_val) ws_val[phys] = in_val[link];
     }
 }
 
-// RWR_X_BLOCKS=<B> (2..64): probe knob, off by default
-static int x_blocks_wanted() {
-    const char* e = getenv("RWR_X_BLOCKS");
-    if (!e) return 1;
-    const int v = atoi(e);
+// rwr_opts.x_blocks (0 = auto, 1 = off, 2..64 = forced); the probe knob RWR_X_BLOCKS=<B> overrides it.  Auto is off: a
+// slice of C4 (x = 400 MB) runs at the same L1TEX bound with and without blocking (profiles/r02_c4slice_*), the padding
+// links of the empty virtual rows cost more than the L2 misses they remove.
+static int x_blocks_wanted(const rwr_graph* g) {
+    int v = g->opts.x_blocks;
+    if (const char* e = getenv("RWR_X_BLOCKS")) v = atoi(e);
     return (v >= 2 && v <= 64) ? v : 1;
 }
 
@@ -214,7 +236,7 @@ void stream_prepare(rwr_graph* g) {
     g->v_rows = g->row_end - g->row_begin;
     g->x_block_size = n;
     {
-        const int want = x_blocks_wanted();
+        const int want = x_blocks_wanted(g);
         const int R = g->v_rows;
         if (want > 1 && R > 0) {
             const u32 block_size = (u32)((((size_t)n + want - 1) / want + 15) & ~(size_t)15);
@@ -257,6 +279,23 @@ void stream_prepare(rwr_graph* g) {
         }
     }
     const bool blocked = g->x_blocks > 1;
+    // hub table of a partitioned graph (see HubMap): the same entry count for both precisions, the FP64 carve-out step
+    HubMap hm{};
+    g->part_hub = 0;
+    g->part_hub_seg = 0;
+    if (parts > 1 && parts <= 8 && g->opts.hub_entries != 0 && (int)g->part_hot.size() == parts && !getenv("RWR_PART_NO_HUB")) {
+        long cap = g->opts.hub_entries > 0 ? (long)g->opts.hub_entries : (long)((WS_HUB_AUTO_BYTES - WS_HDR) / 8);
+        if ((size_t)g->max_smem_optin > (size_t)WS_HDR) cap = std::min<long>(cap, (long)(((size_t)g->max_smem_optin - WS_HDR) / 8));
+        long seg = cap / parts;
+        for (int r = 0; r < parts; r++) seg = std::min<long>(seg, (long)g->part_hot[r]);
+        seg &= ~3L;
+        if (seg > 0) {
+            hm.parts = parts; hm.seg_len = (int)seg; hm.H = (int)seg * parts;
+            for (int r = 0; r < parts; r++) hm.start[r] = g->part_rows[r];
+            g->part_hub = hm.H;
+            g->part_hub_seg = hm.seg_len;
+        }
+    }
     // tile size: WS_TILE links, but smaller graphs (the reference's ego networks) get smaller tiles so that their links
     // still spread over every warp of every SM (big_x_probe.py with RWR_TILE_LINKS: 3.9 M links 39 / 42 / 59 us per
     // iteration with 512 / 1024 / 4096-link tiles, 19.8 M links 92 / 84 / 96 us, 61 M links 244 / 214 / 208 us)
@@ -278,13 +317,13 @@ void stream_prepare(rwr_graph* g) {
         const int V = g->x_blocks * g->v_rows;
         if (padded)
             k_ws_fill_blocked<<<div_up(padded, 256), 256, 0, st>>>(ptr2v.p, cnt_ptr.p, perm_sorted, g->in_src.p + link_base,
-                                                                  valued ? g->in_val64.p + link_base : nullptr, V, n, nnz2, padded,
+                                                                  valued ? g->in_val64.p + link_base : nullptr, V, n, nnz2, padded, hm,
                                                                   g->ws_src.p, valued ? g->ws_val64.p : nullptr);
         k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2v.p, V, 0u, V, n_tiles, (u32)tile_links, g->ws_tile.p);
     } else {
         if (padded)
             k_ws_fill<<<div_up(padded, 256), 256, 0, st>>>(ptr2.p, g->in_ptr.p, g->in_src.p, valued ? g->in_val64.p : nullptr, n, q0,
-                                                          nnz2, padded, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+                                                          nnz2, padded, hm, g->ws_src.p, valued ? g->ws_val64.p : nullptr);
         k_ws_tiles<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2.p, n, q0, g->row_end, n_tiles, (u32)tile_links, g->ws_tile.p);
     }
     KERNEL_CHECK();
@@ -300,6 +339,7 @@ void stream_prepare(rwr_graph* g) {
 // Auto therefore stops at the 100 KB carve-out step in FP64 (~156 KB of L1 left) and at the 164 KB step in FP32,
 // the best points of the sweep on the C2 graph.
 int ws_hub_entries(const rwr_graph* g, int precision) {
+    if (dist_n_ranks(g->comm) > 1) return g->part_hub;     // fixed at build time: the stream encodes the table slots
     const size_t elt = precision == RWR_FP32 ? 4 : 8;
     if ((size_t)g->max_smem_optin <= (size_t)WS_HDR) return 0;
     long cap = (long)(((size_t)g->max_smem_optin - WS_HDR) / elt) & ~3L;
@@ -307,7 +347,7 @@ int ws_hub_entries(const rwr_graph* g, int precision) {
     long want = g->opts.hub_entries < 0 ? std::min(cap, auto_cap) : std::min<long>(cap, (long)g->opts.hub_entries & ~3L);
     // when x is far beyond L2 (or the labels are dealt over the slices of a partitioned graph, where the hottest sources
     // are no longer a label prefix) the table is not worth the L1 it takes: big_x_probe.py, +12 % in FP32 without it
-    if (g->opts.hub_entries < 0 && ((size_t)g->n * elt > ((size_t)160 << 20) || dist_n_ranks(g->comm) > 1)) want = 0;
+    if (g->opts.hub_entries < 0 && (size_t)g->n * elt > ((size_t)160 << 20)) want = 0;
     long n4 = ((long)g->n + 3) & ~3L;
     return (int)std::max<long>(0, std::min(want, n4));
 }
@@ -336,7 +376,7 @@ __device__ __forceinline__ void ws_ldg_if(float& v, int s, int hub, const float*
                  : "+f"(v) : "r"(s), "r"(hub), "l"(addr), "l"(pol));
 }
 
-template <typename T>
+template <typename T, bool DBG>
 __device__ __forceinline__ void ws_gather_stage(const IterParams<T>& p, const int4 (&iv)[WS_R], u64 hub_gen, u32 hub_addr,
                                                 u64 pol_keep, u64 pol_stream, T (&v)[WS_R][4]) {
     int s[WS_R][4];
@@ -344,7 +384,7 @@ __device__ __forceinline__ void ws_gather_stage(const IterParams<T>& p, const in
     for (int j = 0; j < WS_R; j++) {
         s[j][0] = iv[j].x & 0x7fffffff; s[j][1] = iv[j].y & 0x7fffffff; s[j][2] = iv[j].z & 0x7fffffff; s[j][3] = iv[j].w & 0x7fffffff;
     }
-    if (p.debug >= 3) {                 // measurement only: 3 = no gathers, 4 = every gather from the hub, 5 = every gather from L2
+    if (DBG && p.debug >= 3) {          // probe instantiation only: 3 = no gathers, 4 = every gather from the hub, 5 = every gather from L2
 #pragma unroll
         for (int j = 0; j < WS_R; j++)
 #pragma unroll
@@ -387,12 +427,12 @@ struct WsState {
 // One stage of WS_STAGE links: this lane owns 8 consecutive links of the stream (the build stores a stage lane-major
 // so that the two int4 loads stay coalesced); e = their end-of-row flags (bit k), v = their products in storage order.
 // Registers and shuffles only: a load here would sit behind every gather already queued in the SM's L1TEX FIFO.
-template <typename T>
+template <typename T, bool DBG>
 __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, const u32 e, const double (&v)[8], const int lane,
                                            const u32 lt, const u32 le, const u64 pol_first) {
     const u32 FULL = 0xffffffffu;
     const u32 H = __ballot_sync(FULL, e != 0);
-    if (H == 0 || p.debug == 1) {
+    if (H == 0 || (DBG && p.debug == 1)) {
         // inside one long row: per-lane partial, no cross-lane traffic
         const double a = __dadd_rn(__dadd_rn(v[0], v[1]), __dadd_rn(v[2], v[3]));
         const double b = __dadd_rn(__dadd_rn(v[4], v[5]), __dadd_rn(v[6], v[7]));
@@ -438,7 +478,7 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
         acc = __dadd_rn(acc, v[k]);
         if (e & (1u << k)) {
             if (s.cont && row == s.first_row) p.head_partial[s.tile] = acc;
-            else if (p.debug != 2) st_policy(p.y + row, (T)acc, pol_first);
+            else if (!DBG || p.debug != 2) st_policy(p.y + row, (T)acc, pol_first);
             row++;
             acc = 0.0;
         }
@@ -450,7 +490,9 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
 // fit without spills (+4.5 % there; 20 warps cost FP64 7 %: more sectors in flight than the L1 side holds).
 template <typename T, bool VALUED> struct WsCfg { static constexpr int WARPS = (sizeof(T) == 4 && !VALUED) ? 20 : WS_WARPS; };
 
-template <typename T, bool VALUED>
+// DBG: the probe instantiation (rwr_profile_iteration with RWR_DEBUG_MODE) carries the ablation branches; the production
+// instantiation compiles none of them.
+template <typename T, bool VALUED, bool DBG>
 __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(const IterParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (p.ctl->done) return;
@@ -464,13 +506,20 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
 
     if (threadIdx.x == 0) mbar_init(reinterpret_cast<u64*>(smem_raw), 1);
     __syncthreads();
-    if (p.hub > 0 && threadIdx.x == 0) {      // hub table: the first `hub` entries of x, TMA bulk copies (UBLKCP)
+    if (p.hub_segs > 0) {                     // partitioned graph: the hottest labels of every slice, segment after segment
+        T* hub = reinterpret_cast<T*>(smem_raw + WS_HDR);
+        for (int i = threadIdx.x; i < p.hub; i += blockDim.x) {
+            const int sg = i / p.hub_seg_len;
+            hub[i] = p.xhub[p.hub_start[sg] + (i - sg * p.hub_seg_len)];
+        }
+        __syncthreads();
+    } else if (p.hub > 0 && threadIdx.x == 0) {      // hub table: the first `hub` entries of x, TMA bulk copies (UBLKCP)
         const u32 bytes = (u32)p.hub * (u32)sizeof(T);
         mbar_expect_tx(reinterpret_cast<u64*>(smem_raw), bytes);
         for (u32 off = 0; off < bytes; off += 32768) {
             const u32 len = bytes - off < 32768 ? bytes - off : 32768;
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hub_addr + off),
-                         "l"(reinterpret_cast<const unsigned char*>(p.x) + off), "r"(len), "r"(smem0)
+                         "l"(reinterpret_cast<const unsigned char*>(p.xhub) + off), "r"(len), "r"(smem0)
                          : "memory");
         }
     }
@@ -507,8 +556,8 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
         }
         u32 meta_cur = p.ws_tile[cur];
         u32 meta_nxt = p.ws_tile[nxt < n_tiles ? nxt : n_tiles];
-        if (p.hub > 0) mbar_wait_a(smem0, 0);
-        ws_gather_stage<T>(p, ivA, hub_gen, hub_addr, pol_keep, pol_stream, gA);
+        if (p.hub > 0 && p.hub_segs == 0) mbar_wait_a(smem0, 0);
+        ws_gather_stage<T, DBG>(p, ivA, hub_gen, hub_addr, pol_keep, pol_stream, gA);
         if (VALUED) {
 #pragma unroll
             for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + posA + j * WS_STEP, pol_stream, wA[j]);
@@ -534,7 +583,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
         WCLK_LAND_IDX(fl, IVY)                                                                                         \
         WCLK(0);                                                                                                       \
         /* gathers of the next stage, then the indices of the one after it into the registers just freed */            \
-        ws_gather_stage<T>(p, IVY, hub_gen, hub_addr, pol_keep, pol_stream, GY);                                       \
+        ws_gather_stage<T, DBG>(p, IVY, hub_gen, hub_addr, pol_keep, pol_stream, GY);                                  \
         if (VALUED) {                                                                                                  \
             _Pragma("unroll") for (int j = 0; j < WS_R; j++) load4_stream(p.ws_val + POSY + j * WS_STEP, pol_stream, WY[j]); \
         }                                                                                                              \
@@ -558,7 +607,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
             _Pragma("unroll") for (int j = 0; j < WS_R; j++)                                                           \
                 _Pragma("unroll") for (int i = 0; i < 4; i++)                                                          \
                     v[j * 4 + i] = VALUED ? (double)mul_rn(GX[j][i], WX[j][i]) : (double)GX[j][i];                     \
-            ws_consume<T>(p, s, fl, v, lane, lt, le, pol_stream);                                                      \
+            ws_consume<T, DBG>(p, s, fl, v, lane, lt, le, pol_stream);                                                 \
         }                                                                                                              \
         WCLK(4);                                                                                                       \
         if ((ST) == spt - 1) {                                                                                         \
@@ -585,7 +634,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
 #ifdef RWR_PROFILE_CLOCKS
         if (clk_sink == -1.0) p.carry[0] = clk_sink;
 #endif
-    } else if (p.hub > 0 && threadIdx.x == 0) {
+    } else if (p.hub > 0 && p.hub_segs == 0 && threadIdx.x == 0) {
         // the thread that issued the bulk copies drew no tile (every tile was taken before this CTA started): a CTA must
         // not exit with a copy into its shared memory still in flight
         mbar_wait_a(smem0, 0);
@@ -703,19 +752,25 @@ template <typename T>
 void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     const size_t smem = (size_t)WS_HDR + (size_t)p.hub * sizeof(T);
-    auto kern = valued ? k_spmv_ws<T, true> : k_spmv_ws<T, false>;
+    auto kern = p.debug ? (valued ? k_spmv_ws<T, true, true> : k_spmv_ws<T, false, true>)
+                        : (valued ? k_spmv_ws<T, true, false> : k_spmv_ws<T, false, false>);
     const int threads = (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS) * 32;
     // the opt-in ceiling is a per-function, per-device setting shared by every handle and thread: always the device
     // maximum (a per-launch value would race between threads whose graphs have different hub sizes); the carve-out a
     // launch gets still follows the dynamic size it asks for
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem_optin));
-    if (p.x_blocks > 1) {                         // the row sums of the virtual rows go to yv
-        IterParams<T> pv = p;
-        pv.y = p.yv;
-        kern<<<ws_main_grid(g), threads, smem, g->stream>>>(pv);
-    } else {
-        kern<<<ws_main_grid(g), threads, smem, g->stream>>>(p);
+    IterParams<T> pv = p;
+    pv.xhub = p.x;
+    pv.hub_segs = 0;
+    pv.hub_seg_len = 1;
+    if (g->part_hub > 0 && p.hub == g->part_hub) {          // partitioned graph: segmented hub table, shifted gather vector
+        pv.hub_segs = (int)g->part_hot.size();
+        pv.hub_seg_len = g->part_hub_seg;
+        for (int r = 0; r < pv.hub_segs; r++) pv.hub_start[r] = g->part_rows[r];
+        pv.x = p.x - g->part_hub;
     }
+    if (p.x_blocks > 1) pv.y = p.yv;              // the row sums of the virtual rows go to yv
+    kern<<<ws_main_grid(g), threads, smem, g->stream>>>(pv);
     KERNEL_CHECK();
 }
 template <typename T>

@@ -1,67 +1,82 @@
-"""Experiment-style evaluation (TweetRecommender/Experiment.cs:69-138, DataLoader.cs:122-140) on flattened link arrays:
-hold out the newest likes of the test users, recommend on the remaining graph, score the lists.
+"""Experiment-style evaluation -- the caller of the hot path (TweetRecommender/Experiment.cs:31-155, DataLoader.cs:79-140).
 
-Host-side data preparation only (numpy); every recommendation runs through the C ABI (`Recommender.RecommendationBatch`).
+Host driver only: the k-fold hold-out (`Graph.hold_out` -> rwr_graph_hold_out), the methodology masks
+(rwr_methodology_masks), the graph build, the recommendations and the hit / average-precision arithmetic
+(`evaluate_users` -> rwr_evaluate_users) all run on the device through the C ABI.
 """
 from __future__ import annotations
 
-from typing import Dict, Sequence, Tuple
+from typing import Dict, Optional, Sequence
 
 import numpy as np
 
-from .rwr import EdgeType, NodeType
+from .rwr import FP64, EdgeType, Graph, Methodology, NodeType, evaluate_users, methodology_options
 
 
-def hold_out_likes(links: Dict[str, np.ndarray], test_users: Sequence[int], fraction: float = 0.1):
-    """For every test user the upper `fraction` (by tweet id, i.e. the newest -- DataLoader.cs:126-137 takes the last fold
-    of the id-ordered likes) of the user's LIKE links leaves the graph in both directions and becomes the user's test set.
-
-    -> (links without the held-out pairs, {user: int64 array of held-out tweet ids})."""
-    src, dst, et = links["src"], links["dst"], links["etype"]
-    node_id, node_type = links["node_id"], links["node_type"]
-    n = len(node_id)
-    drop = np.zeros(len(src), bool)
-    test: Dict[int, np.ndarray] = {}
-    like = et == EdgeType.LIKE
-    order = np.argsort(src, kind="stable")
-    starts = np.searchsorted(src[order], np.arange(n + 1))
-    pair_key = src.astype(np.int64) * n + dst
-    held_keys = []
-    for u in test_users:
-        rows = order[starts[u]:starts[u + 1]]
-        rows = rows[like[rows] & (node_type[dst[rows]] == NodeType.ITEM)]
-        if len(rows) == 0:
-            test[int(u)] = np.zeros(0, np.int64)
-            continue
-        ids = node_id[dst[rows]]
-        k = int(len(rows) * fraction)
-        if k == 0:
-            test[int(u)] = np.zeros(0, np.int64)
-            continue
-        newest = rows[np.argsort(ids, kind="stable")[-k:]]
-        test[int(u)] = np.sort(node_id[dst[newest]])
-        drop[newest] = True
-        held_keys.append(dst[newest].astype(np.int64) * n + u)          # the reverse links tweet -> user
-    if held_keys:
-        hk = np.unique(np.concatenate(held_keys))
-        rev = like & np.isin(pair_key, hk)
-        drop |= rev
-    keep = ~drop
-    out = dict(links)
-    for k_ in ("src", "dst", "etype", "w"):
-        out[k_] = links[k_][keep]
-    return out, test
+def like_count(links: Dict[str, np.ndarray], user: int) -> int:
+    """`loader.cntLikesOfEgoUser` (DataLoader.cs:94-109): the tweets the user likes, before any split."""
+    sel = (links["src"] == user) & (links["etype"] == EdgeType.LIKE)
+    return int((links["node_type"][links["dst"][sel]] == NodeType.ITEM).sum())
 
 
-def recall_at_k(ids: np.ndarray, counts: np.ndarray, users: Sequence[int], test: Dict[int, np.ndarray]) -> Tuple[float, int, int]:
-    """-> (mean recall@k over the users with a non-empty test set, total hits, users counted)."""
-    total, hits_all, counted = 0.0, 0, 0
-    for i, u in enumerate(users):
-        t = test.get(int(u))
-        if t is None or len(t) == 0:
-            continue
-        hits = int(np.isin(ids[i, :counts[i]], t).sum())
-        total += hits / len(t)
-        hits_all += hits
-        counted += 1
-    return (total / counted if counted else 0.0), hits_all, counted
+def ego_network_is_valid(links: Dict[str, np.ndarray], ego: int, n_folds: int) -> bool:
+    """`DataLoader.checkEgoNetworkValidation` (DataLoader.cs:79-92): >= nFolds and >= 50 likes, >= 50 friends."""
+    likes = like_count(links, ego)
+    friends = int(((links["src"] == ego) & (links["etype"] == EdgeType.FRIENDSHIP)).sum())
+    return not (likes < n_folds or likes < 50 or friends < 50)
+
+
+def result_row(ego_id: int, methodology: int, n_folds: int, n_iter: int, hits: float, cnt_likes: int, sum_ap: float) -> str:
+    """One line of result.dat (Experiment.cs:144-152; read back as 7 tab-separated tokens at Program.cs:41):
+    ego \\t methodology \\t nFolds \\t nIterations \\t (int)HIT \\t cntLikes \\t AVGPRECISION / nFolds."""
+    return "\t".join([str(int(ego_id)), str(int(methodology)), str(int(n_folds)), str(int(n_iter)), str(int(hits)),
+                      str(int(cnt_likes)), "%.15g" % (sum_ap / n_folds)])      # .NET double.ToString() == "G15"
+
+
+def run_k_fold(links: Dict[str, np.ndarray], methodology: int = Methodology.ALL, n_folds: int = 10, n_iter: int = 20,
+               ego: int = 0, precision: int = FP64, validate: bool = True, **graph_opts) -> Optional[dict]:
+    """`Experiment.runKFoldCrossValidation` for one ego network and one methodology (Experiment.cs:46-155).  `links` is the
+    network with every relation loaded (Methodology.ALL); the methodology's feature set is applied as link-type masks.
+    Per fold: hold out the ego's fold (device), buildGraph (device), Recommendation(ego, 0.15f, nIterations) and the
+    walk over the full ranking (device).  -> dict(row=<result.dat line>, hits, map, cnt_likes, folds=[...]) or None when
+    the network fails `checkEgoNetworkValidation` (Experiment.cs:72-74)."""
+    if validate and not ego_network_is_valid(links, ego, n_folds):
+        return None
+    cnt_likes = like_count(links, ego)
+    opts = dict(methodology_options(methodology))
+    opts.update(graph_opts)
+    hits, sum_ap, folds = 0.0, 0.0, []
+    for fold in range(n_folds):
+        g = Graph.from_arrays(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"], **opts)
+        try:
+            test = g.hold_out([ego], n_folds, fold)
+            g.buildGraph()
+            r = evaluate_users(g, None, None, 0.15, n_iter, k=10, precision=precision)
+        finally:
+            g.close()
+        hits += int(r["hits"][0])                      # finalResult[HIT] += nHits           (Experiment.cs:134)
+        sum_ap += float(r["avg_precision"][0])         # finalResult[AVGPRECISION] += ...    (Experiment.cs:136)
+        folds.append(dict(fold=fold, n_test=len(test[int(ego)]), hits=int(r["hits"][0]), avg_precision=float(r["avg_precision"][0])))
+    ego_id = int(links["node_id"][ego])
+    return dict(row=result_row(ego_id, methodology, n_folds, n_iter, hits, cnt_likes, sum_ap), hits=int(hits),
+                map=sum_ap / n_folds, cnt_likes=cnt_likes, folds=folds)
+
+
+def evaluate_hold_out(graph: Graph, users: Sequence[int], n_folds: int = 10, fold: int = 9, n_iter: int = 20, k: int = 10,
+                      precision: int = FP64) -> dict:
+    """BASELINE config 5: one global hold-out for many test users of one graph (the newest tenth of every user's likes with
+    the defaults), then top-k / full-ranking metrics for all of them.  `graph` must be created but not built.
+    -> dict(recall_at_k, hits_at_k, users_counted, mean_avg_precision, hits, seeds_per_s, ...)."""
+    graph.hold_out(users, n_folds, fold)
+    graph.buildGraph()
+    r = evaluate_users(graph, None, None, 0.15, n_iter, k=k, precision=precision)
+    return summarize(r)
+
+
+def summarize(r: dict) -> dict:
+    has = r["n_test"] > 0
+    counted = int(has.sum())
+    recall = float((r["hits_at_k"][has] / r["n_test"][has]).mean()) if counted else 0.0
+    return dict(recall_at_k=recall, hits_at_k=int(r["hits_at_k"].sum()), users_counted=counted,
+                mean_avg_precision=float(r["avg_precision"][has].mean()) if counted else 0.0, hits=int(r["hits"].sum()),
+                n_test=int(r["n_test"].sum()), total_ms=float(r["info"].total_ms), iterate_ms=float(r["info"].iterate_ms))

@@ -98,14 +98,59 @@ class SynthSpec(dict):
         return N.rwr_synth_spec(**{k: int(d[k]) for k in self.FIELDS})
 
 
+class Methodology(enum.IntEnum):   # TweetRecommender/Experiment.cs:7-15
+    BASELINE = 0
+    INCL_FRIENDSHIP = 1
+    INCL_FOLLOWSHIP_ON_THIRDPARTY = 2
+    INCL_AUTHORSHIP = 3
+    INCL_MENTIONCOUNT = 4
+    INCL_ALLFOLLOWSHIP = 5
+    INCL_FRIENDSHIP_AUTHORSHIP = 6
+    INCL_FRIENDSHIP_MENTIONCOUNT = 7
+    ALL = 8
+    EXCL_FRIENDSHIP = 9
+    EXCL_FOLLOWSHIP_ON_THIRDPARTY = 10
+    EXCL_AUTHORSHIP = 11
+    EXCL_MENTIONCOUNT = 12
+    INCL_FOLLOWSHIP_ON_THIRDPARTY_AND_AUTHORSHIP = 13
+    INCL_FOLLOWSHIP_ON_THIRDPARTY_AND_MENTIONCOUNT = 14
+    INCL_AUTHORSHIP_AND_MENTIONCOUNT = 15
+
+
+class Feature(enum.IntEnum):       # TweetRecommender/Experiment.cs:16
+    FRIENDSHIP = 0
+    FOLLOWSHIP_ON_THIRDPARTY = 1
+    AUTHORSHIP = 2
+    MENTIONCOUNT = 3
+
+
+def methodology_masks(methodology: int) -> Tuple[List[Feature], int, int]:
+    """`DataLoader.graphConfiguration(Methodology, fold)` (DataLoader.cs:142-219) + the FRIENDSHIP -> UNDEFINED rewrite of
+    Experiment.cs:84-101, as masks over a graph that carries every relation -> (features, undefined_type_mask,
+    zero_weight_type_mask); the table itself lives in the native library (rwr_methodology_masks)."""
+    f, u, z = C.c_int32(), C.c_int32(), C.c_int32()
+    _check(N.lib().rwr_methodology_masks(int(methodology), C.byref(f), C.byref(u), C.byref(z)))
+    return [x for x in Feature if f.value >> int(x) & 1], u.value, z.value
+
+
+def methodology_options(methodology: int) -> dict:
+    """Keyword options for `Graph(...)` that turn a full graph into the graph of `methodology`."""
+    _, u, z = methodology_masks(methodology)
+    return dict(undefined_types=[t for t in EdgeType if u >> int(t) & 1], zero_weight_types=[t for t in EdgeType if z >> int(t) & 1])
+
+
 def _opts(device=-1, layout=N.LAYOUT_AUTO, relabel=True, hub_entries=-1, batch_width=0, stream=0, kernel=0,
-          hot_min_degree=0, undefined_types=()) -> N.rwr_opts:
+          hot_min_degree=0, undefined_types=(), zero_weight_types=(), x_blocks=0, empty_seed_ok=False) -> N.rwr_opts:
     mask = 0
     for t in undefined_types:            # EdgeType values that count as UNDEFINED at buildGraph() (Experiment.cs:84-101)
         mask |= 1 << int(t)
+    zmask = 0
+    for t in zero_weight_types:          # EdgeType values whose links keep their slot with weight 0.0 (Methodology 15)
+        zmask |= 1 << int(t)
     return N.rwr_opts(device=int(device), layout=int(layout), relabel=0 if relabel else 1, hub_entries=int(hub_entries),
                       batch_width=int(batch_width), kernel=int(kernel), stream=int(stream),
-                      hot_min_degree=int(hot_min_degree), undefined_type_mask=mask)
+                      hot_min_degree=int(hot_min_degree), undefined_type_mask=mask, zero_weight_type_mask=zmask,
+                      x_blocks=int(x_blocks), empty_seed_ok=1 if empty_seed_ok else 0, reserved=0)
 
 
 class Comm:
@@ -149,6 +194,9 @@ class Graph:
         self.nodes = nodes
         self.edges = edges
         if nodes is not None:
+            # `edges[seed]` throws for a MISSING key only (Recommender.cs:21): an entry with an empty list is served.  The
+            # flattened arrays cannot tell the two apart, so the dictionary form checks the key itself (Recommender below)
+            self._opts = dict(opts, empty_seed_ok=True)
             n = len(nodes)
             node_id = np.fromiter((nodes[i].id for i in range(n)), np.int64, n)
             node_type = np.fromiter((nodes[i].type for i in range(n)), np.int32, n)
@@ -230,6 +278,30 @@ class Graph:
         val = np.empty(i.nnz, np.float64)
         _check(N.lib().rwr_graph_get_csr(self._h, _p(rp), _p(col), _p(val)))
         return rp, col, val
+
+    def csr_types(self) -> np.ndarray:
+        """`graph[i][k].type` of every explicit link, CSR order (Graph.cs:73-74 keeps the whole ForwardLink)."""
+        i = self.info()
+        if not i.built:
+            raise KeyError("buildGraph() has not run")
+        t = np.empty(i.nnz, np.int32)
+        _check(N.lib().rwr_graph_get_csr_types(self._h, _p(t)))
+        return t
+
+    def hold_out(self, users: Sequence[int], n_folds: int, fold: int) -> Dict[int, np.ndarray]:
+        """`DataLoader.splitLikeHistory` (DataLoader.cs:122-140) on the device for every user of `users`: the LIKE links
+        (both directions) of the fold's tweets leave `edges`; -> {user: held-out tweet ids, ascending} (`loader.testSet`).
+        Call before buildGraph()."""
+        u = np.ascontiguousarray(users, np.int32)
+        if len(u) and (u.min() < 0 or u.max() >= self.size()):
+            raise KeyError("user outside the node range")
+        cap = int(self.degrees(raw=True)[u].sum()) if len(u) else 0     # a user's test set is a subset of its raw links
+        ptr = np.zeros(len(u) + 1, np.int64)
+        ids = np.empty(max(cap, 1), np.int64)
+        total = C.c_int64()
+        _check(N.lib().rwr_graph_hold_out(self._h, _p(u), len(u), int(n_folds), int(fold), _p(ptr), _p(ids), cap, C.byref(total)))
+        self.test_users, self.test_ptr, self.test_ids = u, ptr, ids[:total.value].copy()
+        return {int(x): self.test_ids[ptr[i]:ptr[i + 1]] for i, x in enumerate(u)}
 
     def degrees(self, raw: bool = False) -> np.ndarray:
         n = self.info().n_nodes
@@ -329,6 +401,7 @@ class Model:
         self._fixed_total = 0
         self._res: Optional[_Result] = None
         self.residual = float("nan")
+        self.nextRank = np.zeros(self.nNodes)         # Model.cs:8
 
     def _seed(self) -> int:
         return -1 if self.targetNode is None else int(self.targetNode)
@@ -347,6 +420,34 @@ class Model:
         self._res, it = run_threshold(self.graph, [self._seed()], self.dampingFactor, thr, max_iter, self.precision)
         self.nIterations = int(it[0])
         self.residual = self._res.info().residual
+
+    # -- the step methods of Model.cs:76-115.  Nobody in the reference calls them one by one; here each deliverRanks()
+    #    re-runs the device loop from the constructor state (O(step) per call) so that the surface stays usable.
+    @property
+    def restart(self) -> np.ndarray:      # Model.cs:9, :25, :45-48
+        r = np.zeros(self.nNodes)
+        if self.targetNode is None:
+            r[:] = 1.0 / self.nNodes
+        else:
+            r[self.targetNode] = 1.0
+        return r
+
+    def deliverRanks(self) -> None:
+        res = run_fixed(self.graph, [self._seed()], self.dampingFactor, self._fixed_total + 1, self.precision)
+        self.nextRank = res.scores(0)
+        res.close()
+
+    def updateRanks(self) -> None:
+        self._fixed_total += 1
+        self.nIterations = self._fixed_total
+        self._res = run_fixed(self.graph, [self._seed()], self.dampingFactor, self._fixed_total, self.precision)
+        self.nextRank = np.zeros(self.nNodes)
+
+    def checkConvergence(self, threshold: float) -> bool:
+        diff = 0.0
+        for a, b in zip(self.rank.tolist(), self.nextRank.tolist()):     # sequential, like Model.cs:111-113
+            diff += abs(a - b)
+        return diff < threshold
 
     @property
     def rank(self) -> np.ndarray:
@@ -370,6 +471,8 @@ class Recommender:
                        topN: Optional[int] = None) -> List[Tuple[int, float]]:
         """`dampingFactor` is the reference's C# float: it is widened to double here, as at Recommender.cs:16."""
         c = widen_float(dampingFactor)
+        if self.graph.edges is not None and int(idxTargetUser) not in self.graph.edges:
+            raise KeyError(f"edges has no entry for node {idxTargetUser} (KeyNotFoundException, Recommender.cs:21)")
         if topN is not None and 0 < topN <= 16:
             # fused request path: seed in, top-k (id, score) pairs out, nothing else crosses the boundary
             ids, sc, cnt = self.RecommendationBatch([int(idxTargetUser)], dampingFactor, nIteration, int(topN))
@@ -399,6 +502,34 @@ class Recommender:
                                      self.precision, int(topN), _p(ids), _p(sc), _p(cnt), C.byref(info)))
         self.last_info = info
         return ids, sc, cnt
+
+
+def evaluate_users(graph: Graph, users: Optional[Sequence[int]] = None, test: Optional[Dict[int, Sequence[int]]] = None,
+                   dampingFactor: float = 0.15, nIteration: int = 20, k: int = 10, precision: int = FP64):
+    """Experiment.cs:121-128 for many users on the device (rwr_evaluate_users): for every user the number of hits and the
+    average precision over the FULL ranking `Recommendation(user, dampingFactor, nIteration)`, plus the hits among the first
+    k.  `users` / `test` None: the users and test sets of `graph.hold_out(...)`.
+    -> dict(hits, avg_precision, hits_at_k, n_test: arrays [n_users]; info)"""
+    if users is None:
+        u, ptr, ids = graph.test_users, graph.test_ptr, graph.test_ids
+    else:
+        u = np.ascontiguousarray(users, np.int32)
+        if test is None:
+            t = dict(zip(graph.test_users.tolist(), range(len(graph.test_users))))
+            sets = [graph.test_ids[graph.test_ptr[t[int(x)]]:graph.test_ptr[t[int(x)] + 1]] for x in u]
+        else:
+            sets = [np.asarray(list(test[int(x)]), np.int64) for x in u]
+        ptr = np.zeros(len(u) + 1, np.int64)
+        np.cumsum([len(x) for x in sets], out=ptr[1:])
+        ids = np.ascontiguousarray(np.concatenate(sets) if sets else np.zeros(0), np.int64)
+    ptr = np.ascontiguousarray(ptr, np.int64)
+    ids = np.ascontiguousarray(ids, np.int64)
+    n = len(u)
+    hits = np.zeros(n, np.int32); atk = np.zeros(n, np.int32); nt = np.zeros(n, np.int32); ap = np.zeros(n, np.float64)
+    info = N.rwr_run_info()
+    _check(N.lib().rwr_evaluate_users(graph._h, _p(u), n, _p(ptr), _p(ids) if len(ids) else None, widen_float(dampingFactor),
+                                      int(nIteration), precision, int(k), _p(hits), _p(ap), _p(atk), _p(nt), C.byref(info)))
+    return dict(hits=hits, avg_precision=ap, hits_at_k=atk, n_test=nt, info=info)
 
 
 def evaluate(recommendation: Sequence[Tuple[int, float]], testSet: Iterable[int]) -> Tuple[int, float]:

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(L, name), f"librwr_b200.so does not export {name}"
     assert set(names) == set(N.SYMBOLS), "ctypes table and header disagree"
-    assert L.rwr_abi_version() == 1
+    assert L.rwr_abi_version() == 2
 
 
 def test_struct_layouts(tmp_path):

@@ -507,42 +507,42 @@ def test_rows_without_in_links_and_tile_cuts():
 
 # ------------------------------------------------------------------------------------------ Experiment-style evaluation (C5)
 def test_experiment_style_holdout_evaluation():
-    """Experiment.cs:69-138 in small: hold out the newest 10 % of the test users' likes, recommend top-10 for every
-    test user through the batched path, recall@10 / hits / average precision against the oracle on the same graph."""
-    from recommendersystems_b200.experiment import hold_out_likes, recall_at_k
+    """Experiment.cs:69-138 in small (BASELINE config 5): hold out the newest tenth of the test users' likes on the device,
+    recommend top-10 for every test user through the batched path, recall@10 against the oracle on the same graph."""
+    import experiment_ref as R
     spec = dict(seed=2024, n_users=4_000, n_items=30_000, n_third=200, authorship_per_mille=900, n_like=260_000,
                 n_friend=40_000, n_follow=1_000, n_mention=0, undefined_per_mille=0, scramble=1, p1_byte=61)
     full = O.synth_generate(spec)
     deg_like = np.bincount(full["src"][full["etype"] == 1], minlength=len(full["node_id"]))
     users = np.flatnonzero(deg_like[:spec["n_users"]] >= 20)[:96]
-    links, test = hold_out_likes(full, users, 0.1)
+    links, test = R.hold_out(full, users, 10, 9)
     assert sum(len(t) for t in test.values()) > 200 and len(links["src"]) < len(full["src"])
-    gg = gpu_graph(links)
+    gg = rs.Graph.from_arrays(full["node_id"], full["node_type"], full["src"], full["dst"], full["etype"], full["w"])
+    gtest = gg.hold_out(users, 10, 9)
+    assert all(gtest[int(u)].tolist() == test[int(u)].tolist() for u in users)
+    gg.buildGraph()
     og = oracle_graph(links)
     rec = rs.Recommender(gg)
     ids, sc, cnt = rec.RecommendationBatch(users, 0.15, 15, 10)
-    r_gpu, hits_gpu, counted = recall_at_k(ids, cnt, users, test)
-    assert counted == len(users)
-    # oracle on every test user (small graph): identical lists -> identical recall
-    oids_all = np.zeros_like(ids)
-    ocnt = np.zeros_like(cnt)
+    hits_gpu = hits_cpu = 0
     for i, u in enumerate(users):
         a, b = og.recommend(int(u), 0.15, 15, top_n=10)
         same_ranking(ids[i, :cnt[i]], sc[i, :cnt[i]], a, b)
-        oids_all[i, :len(a)] = a
-        ocnt[i] = len(a)
-    r_cpu, hits_cpu, _ = recall_at_k(oids_all, ocnt, users, test)
-    assert hits_gpu == hits_cpu and abs(r_gpu - r_cpu) < 1e-15
+        hits_gpu += int(np.isin(ids[i, :cnt[i]], test[int(u)]).sum())
+        hits_cpu += int(np.isin(a, test[int(u)]).sum())
+    assert hits_gpu == hits_cpu
     # held-out tweets are recommendable again (they left the exclusion list with their LIKE link)
     assert hits_gpu > 0
+    r = rs.evaluate_users(gg, None, None, 0.15, 15, k=10)
+    assert int(r["hits_at_k"].sum()) == hits_gpu
     # full ranking of two users: hits / average precision as Experiment.cs:121-128 computes them
-    for u in users[:2]:
+    for j, u in enumerate(users[:2]):
         full_rank = rec.Recommendation(int(u), 0.15, 15)
         a, b = og.recommend(int(u), 0.15, 15)
         same_ranking([p[0] for p in full_rank], [p[1] for p in full_rank], a, b)
         h1, ap1 = rs.evaluate(full_rank, test[int(u)])
         h2, ap2 = O.evaluate(a, test[int(u)])
-        assert h1 == h2 == len(test[int(u)]) and abs(ap1 - ap2) <= 1e-12
+        assert h1 == h2 == len(test[int(u)]) == int(r["hits"][j]) and abs(ap1 - ap2) <= 1e-12 and abs(r["avg_precision"][j] - ap2) <= 1e-12
 
 
 # ------------------------------------------------------------------------------------------ concurrency (Program.cs:11, :61-66)
