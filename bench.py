@@ -45,6 +45,23 @@ C4_SPEC = dict(seed=20260104, n_users=5_000_000, n_items=45_000_000, n_third=0, 
                p1_byte=61, reserved=0)
 
 
+# C5 (BASELINE configs[4]): Experiment-style evaluation, 1 M users + 9 M tweets, ~190 M links, one global hold-out of the
+# newest tenth of every test user's likes (DataLoader.cs:122-140 with nFolds = 10, fold = 9), top-10 + full-ranking metrics
+C5_SPEC = dict(seed=20260105, n_users=1_000_000, n_items=9_000_000, n_third=0, authorship_per_mille=1000,
+               n_like=70_000_000, n_friend=20_000_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1,
+               p1_byte=61, reserved=0)
+SPEC_PEAK_GBS = 8000.0          # the HBM figure BASELINE.json's north_star names ("~8 TB/s")
+
+
+def c2_config(n: int, nnz: int, scale: float, world: int) -> dict:
+    """The `config` object of the JSON line: the workload only, identical for both arms (`--impl ours` / `reference`)."""
+    return {"workload": "C2: single-seed RWR, synthetic Twitter-shaped graph (1M users, 10M tweets, power-law, scrambled ids), "
+                        "c=0.15f, 20 iterations",
+            "n_nodes": int(n), "nnz": int(nnz), "scale": scale, "iterations": N_ITER, "top_k": TOP_K,
+            "parallelism": f"independent seeds x{world}, graph replicated, no collective",
+            "l2": "inputs larger than L2: the matrix stream of one iteration (>= 0.8 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
 def scaled_spec(scale: float) -> dict:
     s = dict(C2_SPEC)
     if scale != 1.0:
@@ -231,9 +248,9 @@ def run_ours(args):
         brec.RecommendationBatch(all_bseeds[:16], C_FLOAT, N_ITER, TOP_K)
         barrier()
         t0 = time.perf_counter()
-        brec.RecommendationBatch(bseeds, C_FLOAT, N_ITER, TOP_K)
+        blists = brec.RecommendationBatch(bseeds, C_FLOAT, N_ITER, TOP_K)
         torch.cuda.synchronize()
-        batched[bname] = (time.perf_counter() - t0, brec.last_info.iterate_ms * 1e-3)
+        batched[bname] = (time.perf_counter() - t0, brec.last_info.iterate_ms * 1e-3, blists)
     # ---- C4-style leg (N > 1 only): the SAME graph row-partitioned over the ranks, per-iteration allGather of x
     parted = None
     if dist is not None and not args.no_partitioned:
@@ -243,6 +260,10 @@ def run_ours(args):
         if world >= 8 and args.scale == 1.0:
             pspec = dict(C4_SPEC)                       # BASELINE configs[3]: 50 M nodes, ~2 B links
         parted = partitioned_leg(rs, dist, torch, pspec, rank, world, local, int(seeds[0]), c, precision, args.steps)
+    # ---- C5 leg (BASELINE configs[4]): Experiment-style evaluation, test users sharded over the ranks
+    c5 = None
+    if not args.no_c5:
+        c5 = c5_leg(rs, dist, torch, rank, world, local, args)
     clocks = sampler.stop()
 
     times = torch.tensor([dev_ms, e2e_s * 1e3, iter_ms, batched["fp64"][0], batched["fp32"][0], batched["fp64"][1],
@@ -264,15 +285,20 @@ def run_ours(args):
         peak, peak_src = measured_peak_gbs()
         formula_b, actual_b = algorithmic_bytes(n, nnz, vb, info.layout == N.LAYOUT_INDEX)
         achieved = formula_b / (spmv_ms.value * 1e-3) / 1e9
-        traffic = None
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed `ncu --set full` capture of this
+        # kernel on this graph (a profiler cannot run inside the timed program); null when no capture is committed
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp) and args.scale == 1.0:
             try:
-                traffic = json.load(open(tp)).get(args.precision, {}).get("dram_bytes_per_launch")
+                rec = json.load(open(tp)).get(args.precision, {})
+                traffic, traffic_src = rec.get("dram_bytes_per_launch"), rec.get("source")
             except Exception:   # noqa: BLE001
                 traffic = None
         roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 4), "traffic": traffic, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                    "frac_of_spec_peak": round(achieved / SPEC_PEAK_GBS, 4), "spec_peak": SPEC_PEAK_GBS,
+                    "frac_iteration_of_spec_peak": round(formula_b / ((spmv_ms.value + fix_ms.value) * 1e-3) / 1e9 / SPEC_PEAK_GBS, 4),
                     "kernel": "k_spmv_ws", "kernel_ms": round(spmv_ms.value, 4),
                     "epilogue_kernels_ms": round(fix_ms.value, 4),
                     "frac_iteration": round(formula_b / ((spmv_ms.value + fix_ms.value) * 1e-3) / 1e9 / peak, 4),
@@ -280,21 +306,18 @@ def run_ours(args):
                     "layout": "index-only (row weight folded into x)" if info.layout == N.LAYOUT_INDEX else "valued",
                     "layout_bytes_per_launch": actual_b,
                     "frac_layout": round(actual_b / (spmv_ms.value * 1e-3) / 1e9 / peak, 4)}
-        cpu_baseline = None
+        cpu_baseline, parity = None, None
         if world == 1 and not args.no_cpu:
-            cpu_baseline = cpu_baseline_leg(g, int(seeds[0]), nnz, sample_iters=args.cpu_iters)
+            cpu_baseline, parity = cpu_baseline_leg(g, rs, int(seeds[0]), nnz, args.cpu_iters, bseeds, batched, args.parity_seeds)
         line = {
             "metric": "RWR GTEPS (nnz x iterations x seeds / s), single-seed, 20 iterations",
             "value": round(value, 2), "unit": "GTEPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64" if precision == rs.FP64 else "f32", "data": "synthetic",
-            "config": {"workload": "C2: single-seed RWR, synthetic Twitter-shaped graph (1M users, 10M tweets, "
-                                   "power-law, scrambled ids), c=0.15f, 20 iterations",
-                       "n_nodes": n, "nnz": nnz, "n_links_raw": info.n_links_raw, "scale": args.scale,
-                       "seeds_per_step_per_gpu": 1, "parallelism": f"seed-sharded x{world}, graph replicated, no collective",
-                       "l2": "matrix stream per iteration (>= 0.8 GB) is larger than L2 (126 MB); no explicit flush",
-                       "hub_entries": info.hub_entries_fp64 if precision == rs.FP64 else info.hub_entries_fp32,
-                       "chunks": info.n_chunks, "max_in_degree": info.max_in_degree},
+            "config": c2_config(n, nnz, args.scale, world),
+            "impl_config": {"n_links_raw": info.n_links_raw, "seeds_per_step_per_gpu": 1,
+                            "hub_entries": info.hub_entries_fp64 if precision == rs.FP64 else info.hub_entries_fp32,
+                            "chunks": info.n_chunks, "max_in_degree": info.max_in_degree},
             "gteps_iteration_loop_only": round(edges_total / (iter_ms * 1e-3) / 1e9, 2),
             "other_precision": {"dtype": "f32" if precision == rs.FP64 else "f64",
                                 "value": round(edges_total / (other_ms * 1e-3) / 1e9, 2), "unit": "GTEPS",
@@ -307,6 +330,10 @@ def run_ours(args):
                                     f"top-10 per seed, the seed list sharded x{world} in contiguous blocks (no collective); "
                                     f"host seed list in, top-10 lists out",
                         "seeds_total": args.batch_seeds,
+                        "roofline": {"note": "SURVEY 8(d): E (4 + vb) + 4 (N + 1) + 2 N B vb per matrix pass of B seeds, over the device time "
+                                             "of the passes (k_spmm + k_spmm_fixup), against the measured HBM peak",
+                                     "fp64_frac": round(batched_frac(n, nnz, 8, 8, nb, b64_it), 4),
+                                     "fp32_frac": round(batched_frac(n, nnz, 4, 16, nb, b32_it), 4)},
                         "fp64": {"seeds_per_s": round(args.batch_seeds / b64_s, 1),
                                  "seed_gteps_e2e": round(nnz * N_ITER * args.batch_seeds / b64_s / 1e9, 1),
                                  "seed_gteps_iteration_loop": round(nnz * N_ITER * args.batch_seeds / b64_it / 1e9, 1)},
@@ -314,12 +341,13 @@ def run_ours(args):
                                  "seed_gteps_e2e": round(nnz * N_ITER * args.batch_seeds / b32_s / 1e9, 1),
                                  "seed_gteps_iteration_loop": round(nnz * N_ITER * args.batch_seeds / b32_it / 1e9, 1)}},
             "row_partitioned": parted,
+            "c5": c5,
+            "parity": parity,
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
-            "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1),
-                      "setup_wall_s": round(setup_s, 2), "device_bytes": info.device_bytes},
+            "build": build_record(info, vb=8, setup_s=setup_s),
             "top1": list(last_top[0]) if last_top else None,
         }
     g.close()
@@ -328,6 +356,26 @@ def run_ours(args):
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def batched_frac(n: int, nnz: int, vb: int, width: int, seeds_per_rank: int, iterate_s: float) -> float:
+    passes = -(-seeds_per_rank // width) * N_ITER
+    if passes == 0 or iterate_s <= 0:
+        return 0.0
+    alg = nnz * (4 + vb) + 4 * (n + 1) + 2 * n * width * vb
+    return alg * passes / iterate_s / 1e9 / measured_peak_gbs()[0]
+
+
+def build_record(info, vb: int, setup_s=None) -> dict:
+    """SURVEY 8(d): the transition-matrix build (K1-K5) moves E0 (4+4+1+8) bytes in and 2 x E (4+vb) bytes out (+ O(N));
+    reported as GB/s of that algorithmic figure over the device time of rwr_graph_build."""
+    alg = info.n_links_raw * (4 + 4 + 1 + 8) + 2 * info.nnz * (4 + vb) + 24 * info.n_nodes
+    rec = {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1), "device_bytes": info.device_bytes,
+           "algorithmic_bytes": int(alg), "gbs": round(alg / max(info.build_ms, 1e-6) / 1e6, 1),
+           "frac_of_measured_hbm": round(alg / max(info.build_ms, 1e-6) / 1e6 / measured_peak_gbs()[0], 4)}
+    if setup_s is not None:
+        rec["setup_wall_s"] = round(setup_s, 2)
+    return rec
 
 
 def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precision, steps):
@@ -355,9 +403,28 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     it_ms = float(t)
     top = m.topk(TOP_K)[0][0].tolist()
+    scores_part = m.scores(0) if rank == 0 else None
     m.close()
     g.close()
     comm.close()
+    # parity of the partitioned run: rank 0 runs the same seed on the same graph UNPARTITIONED
+    # (it fits one GPU's 180 GB even at C4) and compares scores and top-10; the other ranks wait at the next barrier
+    parity = None
+    if rank == 0:
+        g1 = rs.Graph.synthetic(spec, device=local)
+        g1.buildGraph()
+        m1 = run_fixed(g1, [seed], c, N_ITER, precision)
+        ref = m1.scores(0)
+        top1 = m1.topk(TOP_K)[0][0].tolist()
+        m1.close()
+        g1.close()
+        nz = ref != 0
+        rel = float((abs(scores_part[nz] - ref[nz]) / ref[nz]).max()) if nz.any() else 0.0
+        parity = {"against": "the same seed on the same graph, unpartitioned, on rank 0's GPU", "max_rel_diff": rel,
+                  "zeros_preserved": bool((scores_part[~nz] == 0).all()), "top10_identical": top == top1,
+                  "tolerance": 1e-12 if precision == rs.FP64 else 1e-5, "ok": bool(rel <= (1e-12 if precision == rs.FP64 else 1e-5) and top == top1)}
+        del ref, scores_part
+    dist.barrier()
     per_iter_ms = it_ms / steps / N_ITER
     gathered = (world - 1) / world * info.n_nodes * vb          # bytes every rank receives per iteration
     # SURVEY 8(d), per GPU: E_p (4 + vb) + 4 (N_p + 1) + N vb + N_p vb
@@ -375,27 +442,158 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
             "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1), "device_bytes": info.device_bytes},
             "nvlink": {"achieved_lower_bound": round(gathered / (per_iter_ms * 1e-3) / 1e9, 1), "peak": 900.0, "unit": "GB/s",
                        "note": "bytes received per rank / whole iteration time (SpMV slice + epilogue with peer stores + allReduce)"},
-            "seed": seed, "top10_head": top[:3]}
+            "seed": seed, "top10_head": top[:3], "parity": parity}
 
 
-def cpu_baseline_leg(g, seed: int, nnz: int, sample_iters: int):
+def c5_leg(rs, dist, torch, rank, world, local, args):
+    """BASELINE configs[4]: `Experiment.cs`-style evaluation on a 10 M-node graph.  One global hold-out (the newest tenth of
+    every test user's likes: DataLoader.splitLikeHistory with nFolds = 10, fold = 9) on the device, then every test user is
+    ranked in seed tiles and hits / average precision over the full ranking and recall@10 are counted on the device.
+    Test users are sharded over the ranks (graph replicated, no collective).  Default size: 2 048 users on one GPU,
+    12 500 per rank otherwise (100 000 users -- the configuration as specified -- at 8 GPUs)."""
+    import numpy as np
+    from recommendersystems_b200.sharding import shard_seeds
+    from recommendersystems_b200.experiment import summarize
+    spec = dict(C5_SPEC)
+    if args.scale != 1.0:
+        for k in ("n_users", "n_items", "n_like", "n_friend"):
+            spec[k] = max(4, int(spec[k] * args.scale))
+    n_users = args.c5_users if args.c5_users > 0 else (2048 if world == 1 else min(100_000, 12_500 * world))
+    t0 = time.perf_counter()
+    g = rs.Graph.synthetic(spec, device=local)
+    raw_deg = g.degrees(raw=True)
+    cand = np.flatnonzero(raw_deg[:spec["n_users"]] >= 20)
+    n_users = min(n_users, len(cand))
+    users = cand[np.unique(np.linspace(0, len(cand) - 1, n_users).astype(np.int64))].astype(np.int32)
+    g.hold_out(users, 10, 9)
+    held = int(g.test_ptr[-1])
+    g.buildGraph()
+    info = g.info()
+    setup_s = time.perf_counter() - t0
+    mine = shard_seeds(users, rank, world)
+    rs.evaluate_users(g, mine[:16], None, C_FLOAT, N_ITER, k=TOP_K)                    # warm-up tile
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = rs.evaluate_users(g, mine, None, C_FLOAT, N_ITER, k=TOP_K)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    has = r["n_test"] > 0
+    acc = torch.tensor([dt, float((r["hits_at_k"][has] / r["n_test"][has]).sum()), float(has.sum()), float(r["hits_at_k"].sum()),
+                        float(r["hits"].sum()), float(r["avg_precision"][has].sum()), float(r["n_test"].sum())],
+                       dtype=torch.float64, device="cuda")
+    mx = acc.clone()
+    if dist is not None:
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    tot = acc.tolist()
+    dt_max = float(mx[0])
+    out = {"workload": f"C5: Experiment-style evaluation, {len(users)} test users on a synthetic graph of {info.n_nodes} nodes / "
+                       f"{info.nnz} links after the hold-out ({held} held-out likes = the newest tenth of every test user's likes), "
+                       f"20 iterations, full-ranking hits / average precision + recall@10, users sharded x{world}",
+           "users": int(len(users)), "seeds_per_s": round(len(users) / dt_max, 1), "seconds": round(dt_max, 2),
+           "recall_at_10": round(tot[1] / max(tot[2], 1.0), 6), "users_counted": int(tot[2]), "hits_at_10": int(tot[3]),
+           "hits_full_ranking": int(tot[4]), "held_out_likes_of_all_users": held, "test_items_evaluated": int(tot[6]),
+           "mean_average_precision": round(tot[5] / max(tot[2], 1.0), 8),
+           "hold_out_and_build_s": round(setup_s, 2), "dtype": "f64"}
+    # oracle agreement on a sample of the test users (rank 0): identical top-10 lists and identical per-user metrics
+    if rank == 0 and not args.no_cpu and args.c5_parity_users > 0:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        import experiment_ref as R
+        sample = mine[:: max(1, len(mine) // args.c5_parity_users)][:args.c5_parity_users]
+        links = g.export_links()                         # `edges` after the hold-out
+        og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+        del links
+        assert og.build() == 0
+        threads = max(1, min(10, os.cpu_count() or 1))
+        t0 = time.perf_counter()
+        oids, _, ocnt = og.recommend_many(sample, C_FLOAT, N_ITER, TOP_K, threads)
+        cpu_s = time.perf_counter() - t0
+        og.close()
+        gids, _, gcnt = rs.Recommender(g).RecommendationBatch(sample, C_FLOAT, N_ITER, TOP_K)
+        tmap = {int(u): i for i, u in enumerate(g.test_users.tolist())}
+        same, hk_gpu, hk_cpu = 0, 0, 0
+        pos = {int(u): i for i, u in enumerate(mine.tolist())}
+        for i, u in enumerate(sample.tolist()):
+            same += int(gids[i, :gcnt[i]].tolist() == oids[i, :ocnt[i]].tolist())
+            t = g.test_ids[g.test_ptr[tmap[u]]:g.test_ptr[tmap[u] + 1]]
+            hk_cpu += int(np.isin(oids[i, :ocnt[i]], t).sum())
+            hk_gpu += int(r["hits_at_k"][pos[u]])
+        out["parity"] = {"against": f"CPU oracle, Recommendation(u, 0.15f, 20, 10) for {len(sample)} of the test users on {threads} threads "
+                                    f"({cpu_s:.1f} s)", "users": int(len(sample)), "top10_lists_identical": same,
+                         "hits_at_10_gpu": hk_gpu, "hits_at_10_oracle": hk_cpu, "ok": bool(same == len(sample) and hk_gpu == hk_cpu)}
+    g.close()
+    if dist is not None:
+        dist.barrier()
+    return out
+
+
+def cpu_baseline_leg(g, rs, seed: int, nnz: int, sample_iters: int, bseeds, batched, parity_seeds: int):
     """The oracle (a port of Model.cs / Recommender.cs) on the SAME graph, collapsed O(E+N) form, one core --
-    the reference iterates one graph on one thread.  Bounded sample: `sample_iters` iterations instead of 20."""
+    the reference iterates one graph on one thread.  Bounded sample: `sample_iters` iterations instead of 20.
+    The same oracle run is the parity check of the bench configurations: transition matrix
+    bit-exact, scores of the sampled iterations, top-10, and the batched (C3) lists of `parity_seeds` seeds."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
     import oracle as O
+    from recommendersystems_b200.rwr import run_fixed
     links = g.export_links()
     og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
     del links
     assert og.build() == 0
+    parity = {"graph": "the full C2 graph of this run"}
+    # (a) A1-A3: Graph.graph on the full graph, bit for bit
+    rp, col, val = g.csr()
+    orp, ocol, oval = og.csr()
+    parity["csr_bit_exact"] = bool(np.array_equal(rp, orp) and np.array_equal(col, ocol) and
+                                   np.array_equal(val.view(np.uint64), oval.view(np.uint64)))
+    del rp, col, val, orp, ocol, oval
+    c = O.widen_float(C_FLOAT)
     t0 = time.perf_counter()
-    og.run(seed, O.widen_float(C_FLOAT), n_iter=sample_iters)
+    want, _ = og.run(seed, c, n_iter=sample_iters)
     dt = time.perf_counter() - t0
+    # (b) A4-A7: Model.run(sample_iters) of the bench seed, FP64 (1e-12 relative, exact zeros) and FP32 (1e-6 normalised L1)
+    m = run_fixed(g, [seed], c, sample_iters, rs.FP64)
+    got = m.scores(0)
+    nz = want != 0
+    parity["fp64"] = {"iterations": sample_iters, "max_rel_err": float((np.abs(got[nz] - want[nz]) / want[nz]).max()),
+                      "zeros_preserved": bool((got[~nz] == 0).all()), "tolerance": 1e-12}
+    ids, _, cnt = m.topk(TOP_K)
+    oids, _ = og.rank_scores(seed, want)
+    parity["fp64"]["top10_identical"] = ids[0, :cnt[0]].tolist() == oids[:TOP_K].tolist()
+    m.close()
+    m = run_fixed(g, [seed], c, sample_iters, rs.FP32)
+    got = m.scores(0)
+    m.close()
+    parity["fp32"] = {"iterations": sample_iters, "normalised_l1": float(np.abs(got / got.sum() - want / want.sum()).sum()), "tolerance": 1e-6}
+    del got, want
+    # (c) C3: the batched lists of the first seeds of the timed run against Recommendation(seed, 0.15f, 20, 10) on the oracle
+    if parity_seeds > 0 and len(bseeds):
+        ps = np.ascontiguousarray(bseeds[:parity_seeds], np.int32)
+        threads = max(1, min(10, os.cpu_count() or 1))
+        t1 = time.perf_counter()
+        oids, osc, ocnt = og.recommend_many(ps, C_FLOAT, N_ITER, TOP_K, threads)
+        cpu_s = time.perf_counter() - t1
+        rec = {"seeds": int(len(ps)), "oracle": f"Recommendation(seed, 0.15f, 20, 10) on {threads} threads, {cpu_s:.1f} s"}
+        for name in ("fp64", "fp32"):
+            gids, gsc, gcnt = batched[name][2]
+            same = sum(int(gids[i, :gcnt[i]].tolist() == oids[i, :ocnt[i]].tolist()) for i in range(len(ps)))
+            k0 = min(int(gcnt[0]), int(ocnt[0]))
+            rel = max(float((np.abs(gsc[i, :min(gcnt[i], ocnt[i])] - osc[i, :min(gcnt[i], ocnt[i])]) /
+                             np.maximum(osc[i, :min(gcnt[i], ocnt[i])], 1e-300)).max()) for i in range(len(ps))) if k0 else 0.0
+            rec[name] = {"top10_lists_identical": same, "max_rel_score_err": rel}
+        parity["batched_c3"] = rec
     og.close()
+    parity["ok"] = bool(parity["csr_bit_exact"] and parity["fp64"]["max_rel_err"] <= 1e-12 and parity["fp64"]["zeros_preserved"]
+                        and parity["fp64"]["top10_identical"] and parity["fp32"]["normalised_l1"] <= 1e-6
+                        and ("batched_c3" not in parity or parity["batched_c3"]["fp64"]["top10_lists_identical"] == parity["batched_c3"]["seeds"]))
     c1 = c1_literal_leg()
-    return {"value": round(nnz * sample_iters / dt / 1e9, 4), "unit": "GTEPS", "cores": 1, "kind": "port", "c1_literal": c1,
-            "sample": f"{sample_iters} of 20 iterations of one seed on the full graph, collapsed O(E+N) form "
-                      f"(the literal O(N^2) restart loops of Model.cs:92-93 are infeasible beyond ~10k nodes), {dt:.1f} s",
-            "host_cores": os.cpu_count()}
+    return ({"value": round(nnz * sample_iters / dt / 1e9, 4), "unit": "GTEPS", "cores": 1, "kind": "port", "c1_literal": c1,
+             "sample": f"{sample_iters} of 20 iterations of one seed on the full graph, collapsed O(E+N) form "
+                       f"(the literal O(N^2) restart loops of Model.cs:92-93 are infeasible beyond ~10k nodes), {dt:.1f} s",
+             "host_cores": os.cpu_count()}, parity)
 
 
 def c1_literal_leg():
@@ -470,9 +668,7 @@ def run_reference(args):
         "value": round(value, 4), "unit": "GTEPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2: single-seed RWR, synthetic Twitter-shaped graph (1M users, 10M tweets, "
-                               "power-law, scrambled ids), c=0.15f, 20 iterations",
-                   "n_nodes": og.n, "nnz": nnz, "scale": args.scale},
+        "config": c2_config(og.n, nnz, args.scale, args.gpus),
         "cpu_baseline": {"value": round(value, 4), "unit": "GTEPS", "cores": threads, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(),
                          "note": "the reference is C# (.NET 4.5.2); no C# toolchain in this image -> oracle port"},
@@ -495,6 +691,10 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--batch-seeds", type=int, default=1024, help="seeds of the batched (C3) leg, all ranks together")
     ap.add_argument("--no-partitioned", action="store_true", help="skip the row-partitioned leg (N > 1)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 (Experiment-style evaluation) leg")
+    ap.add_argument("--c5-users", type=int, default=0, help="test users of the C5 leg, all ranks together (0: 2048 on one GPU, 12500 per rank otherwise)")
+    ap.add_argument("--c5-parity-users", type=int, default=8, help="test users of the C5 leg checked against the CPU oracle (rank 0)")
+    ap.add_argument("--parity-seeds", type=int, default=8, help="seeds of the batched (C3) leg checked against the CPU oracle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
