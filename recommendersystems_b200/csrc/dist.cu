@@ -113,9 +113,15 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // syn
 
 // Two persistent gather vectors per rank, mapped by every peer (one process per GPU -> CUDA IPC handles, exchanged
 // through the communicator itself).  RWR_DIST_NO_P2P=1, more than 8 ranks or a failing mapping fall back to NCCL.
+bool dist_overlap_wanted(const rwr_graph* g) {
+    const rwr_comm* c = g->comm;
+    return c && c->n_ranks >= 2 && c->n_ranks <= 8 && !getenv("RWR_DIST_LEGACY") && !getenv("RWR_DIST_NO_P2P");
+}
+
 void dist_setup_p2p(rwr_graph* g) {
     rwr_comm* c = g->comm;
     g->p2p = false;
+    g->overlap = false;
     if (!c || c->n_ranks < 2 || c->n_ranks > 8 || c->fake || getenv("RWR_DIST_NO_P2P")) return;
     cudaStream_t st = g->stream;
     const int P = c->n_ranks;
@@ -125,33 +131,39 @@ void dist_setup_p2p(rwr_graph* g) {
         g->pool.bytes += (int64_t)bytes;
         CUDA_CHECK(cudaMemsetAsync(g->px[b], 0, bytes, st));
     }
-    // handles: [P][2] x 64 bytes, every rank broadcasts its own pair
+    CUDA_CHECK(cudaMalloc(&g->psync, sizeof(DistSync)));
+    CUDA_CHECK(cudaMemsetAsync(g->psync, 0, sizeof(DistSync), st));
+    // handles: [P][3] x 64 bytes (the two gather vectors, the tag page), every rank broadcasts its own triple
+    constexpr int HB = 3 * 64;
     DevBuf<unsigned char> hb;
-    hb.alloc((size_t)P * 128);
-    std::vector<unsigned char> host((size_t)P * 128, 0);
-    for (int b = 0; b < 2; b++) {
+    hb.alloc((size_t)P * HB);
+    std::vector<unsigned char> host((size_t)P * HB, 0);
+    void* mine[3] = {g->px[0], g->px[1], g->psync};
+    for (int b = 0; b < 3; b++) {
         cudaIpcMemHandle_t h;
-        CUDA_CHECK(cudaIpcGetMemHandle(&h, g->px[b]));
+        CUDA_CHECK(cudaIpcGetMemHandle(&h, mine[b]));
         static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t size");
-        memcpy(host.data() + (size_t)c->rank * 128 + b * 64, &h, 64);
+        memcpy(host.data() + (size_t)c->rank * HB + b * 64, &h, 64);
     }
     CUDA_CHECK(cudaMemcpyAsync(hb.p, host.data(), host.size(), cudaMemcpyHostToDevice, st));
     NcclApi& api = nccl();
     NCCL_CHECK(api.GroupStart());
-    for (int r = 0; r < P; r++) NCCL_CHECK(api.Broadcast(hb.p + (size_t)r * 128, hb.p + (size_t)r * 128, 128, ncclInt8, r, c->comm, st));
+    for (int r = 0; r < P; r++) NCCL_CHECK(api.Broadcast(hb.p + (size_t)r * HB, hb.p + (size_t)r * HB, HB, ncclInt8, r, c->comm, st));
     NCCL_CHECK(api.GroupEnd());
     CUDA_CHECK(cudaMemcpyAsync(host.data(), hb.p, host.size(), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     int ok = 1;
     for (int b = 0; b < 2; b++) g->peer_px[b].assign(P, nullptr);
+    g->peer_psync.assign(P, nullptr);
     for (int r = 0; r < P && ok; r++) {
-        for (int b = 0; b < 2; b++) {
-            if (r == c->rank) { g->peer_px[b][r] = g->px[b]; continue; }
+        for (int b = 0; b < 3; b++) {
+            void** slot = b < 2 ? &g->peer_px[b][r] : &g->peer_psync[r];
+            if (r == c->rank) { *slot = mine[b]; continue; }
             cudaIpcMemHandle_t h;
-            memcpy(&h, host.data() + (size_t)r * 128 + b * 64, 64);
-            if (cudaIpcOpenMemHandle(&g->peer_px[b][r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            memcpy(&h, host.data() + (size_t)r * HB + b * 64, 64);
+            if (cudaIpcOpenMemHandle(slot, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
                 cudaGetLastError();
-                g->peer_px[b][r] = nullptr;
+                *slot = nullptr;
                 ok = 0;
                 break;
             }
@@ -160,27 +172,81 @@ void dist_setup_p2p(rwr_graph* g) {
     // all ranks must agree: one failing mapping anywhere sends everybody to the NCCL path
     DevBuf<double> flag;
     flag.alloc(1);
-    const double mine = ok ? 0.0 : 1.0;
-    CUDA_CHECK(cudaMemcpyAsync(flag.p, &mine, sizeof(double), cudaMemcpyHostToDevice, st));
+    const double mine_bad = ok ? 0.0 : 1.0;
+    CUDA_CHECK(cudaMemcpyAsync(flag.p, &mine_bad, sizeof(double), cudaMemcpyHostToDevice, st));
     NCCL_CHECK(api.AllReduce(flag.p, flag.p, 1, ncclFloat64, ncclSum, c->comm, st));
     double bad = 0.0;
     CUDA_CHECK(cudaMemcpyAsync(&bad, flag.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
     if (bad != 0.0) { dist_release_p2p(g); return; }
     g->p2p = true;
+    if (g->ws_compact && dist_overlap_wanted(g)) {
+        CUDA_CHECK(cudaStreamCreateWithFlags(&g->xstream, cudaStreamNonBlocking));
+        CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fin, cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++) CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_push[b], cudaEventDisableTiming));
+        g->overlap = true;
+    }
+}
+
+void dist_before_iteration(rwr_graph* g, int b) {
+    if (!g->overlap || !g->push_pending[b]) return;
+    CUDA_CHECK(cudaStreamWaitEvent(g->stream, g->ev_push[b], 0));
+    g->push_pending[b] = false;
+}
+
+void dist_push_slice(rwr_graph* g, int b, size_t elt) {
+    if (!g->overlap) return;
+    rwr_comm* c = g->comm;
+    const int P = c->n_ranks, me = c->rank;
+    const size_t off = (size_t)g->row_begin * elt, len = (size_t)(g->row_end - g->row_begin) * elt;
+    DistSync* mine = (DistSync*)g->psync;
+    CUDA_CHECK(cudaEventRecord(g->ev_fin, g->stream));
+    CUDA_CHECK(cudaStreamWaitEvent(g->xstream, g->ev_fin, 0));
+    for (int j = 1; j < P; j++) {
+        const int peer = (me + j) % P;
+        if (len)
+            CUDA_CHECK(cudaMemcpyAsync((unsigned char*)g->peer_px[b][peer] + off, (unsigned char*)g->px[b] + off, len, cudaMemcpyDefault,
+                                       g->xstream));
+        DistSync* theirs = (DistSync*)g->peer_psync[peer];
+        CUDA_CHECK(cudaMemcpyAsync(&theirs->arrive[me], &mine->tag_out[b], sizeof(unsigned long long), cudaMemcpyDefault, g->xstream));
+    }
+    CUDA_CHECK(cudaEventRecord(g->ev_push[b], g->xstream));
+    g->push_pending[b] = true;
+}
+
+void dist_drain_pushes(rwr_graph* g) {
+    if (!g->overlap) return;
+    for (int b = 0; b < 2; b++) dist_before_iteration(g, b);
+}
+
+void dist_barrier(rwr_graph* g) {
+    rwr_comm* c = g->comm;
+    if (!c || c->n_ranks < 2 || c->fake) return;
+    DevBuf<double> d;
+    d.alloc(1);
+    CUDA_CHECK(cudaMemsetAsync(d.p, 0, sizeof(double), g->stream));
+    NCCL_CHECK(nccl().AllReduce(d.p, d.p, 1, ncclFloat64, ncclSum, c->comm, g->stream));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
 }
 
 // Teardown in three steps (collective on a partitioned handle): every rank closes its mappings of the peers' buffers,
 // all ranks meet on the communicator, and only then does each rank free the buffers it exported -- cudaFree of memory a
 // peer still has open through cudaIpcOpenMemHandle is undefined behaviour.
 void dist_release_p2p(rwr_graph* g) {
-    if (!g->px[0] && !g->px[1] && g->peer_px[0].empty() && g->peer_px[1].empty()) { g->p2p = false; return; }
+    if (g->xstream) { cudaStreamSynchronize(g->xstream); cudaStreamDestroy(g->xstream); g->xstream = nullptr; }
+    if (g->ev_fin) { cudaEventDestroy(g->ev_fin); g->ev_fin = nullptr; }
+    for (int b = 0; b < 2; b++) if (g->ev_push[b]) { cudaEventDestroy(g->ev_push[b]); g->ev_push[b] = nullptr; }
+    g->overlap = false;
+    if (!g->px[0] && !g->px[1] && !g->psync && g->peer_px[0].empty() && g->peer_px[1].empty()) { g->p2p = false; return; }
     const int me = dist_rank(g->comm);
     for (int b = 0; b < 2; b++) {
         for (int r = 0; r < (int)g->peer_px[b].size(); r++)
             if (r != me && g->peer_px[b][r]) cudaIpcCloseMemHandle(g->peer_px[b][r]);
         g->peer_px[b].clear();
     }
+    for (int r = 0; r < (int)g->peer_psync.size(); r++)
+        if (r != me && g->peer_psync[r]) cudaIpcCloseMemHandle(g->peer_psync[r]);
+    g->peer_psync.clear();
     rwr_comm* c = g->comm;
     if (c && c->n_ranks > 1 && !c->fake && c->comm && g_nccl.lib && g->px[0]) {
         // px[0] doubles as the 8-byte payload of the barrier: nobody reads it any more
@@ -191,6 +257,7 @@ void dist_release_p2p(rwr_graph* g) {
     }
     for (int b = 0; b < 2; b++)
         if (g->px[b]) { cudaFree(g->px[b]); g->pool.bytes -= (int64_t)(((size_t)g->n + 8) * 8); g->px[b] = nullptr; }
+    if (g->psync) { cudaFree(g->psync); g->psync = nullptr; }
     g->p2p = false;
 }
 

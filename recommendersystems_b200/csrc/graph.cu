@@ -573,8 +573,13 @@ static void graph_build_impl(rwr_graph* g) {
             k_deal_labels<<<grid_for(n), 256, 0, st>>>(tmp.p, n, n_hot, parts, plan, g->old_of_new.p, g->new_of_old.p);
             KERNEL_CHECK();
             CUDA_CHECK(cudaStreamSynchronize(st));
-            g->part_rows.assign(plan.start, plan.start + parts + 1);
+            g->deal_rows.assign(plan.start, plan.start + parts + 1);
             g->part_hot.assign(plan.hot_of, plan.hot_of + parts);
+            // ownership boundaries: the deal's, rounded down to 32 labels, so that a 128-byte line of x (32 floats, 16
+            // doubles) belongs to ONE rank -- the overlapped exchange lets a rank gather from a slice while its neighbour's
+            // slice is still arriving, and a line that spans both would be cached half stale
+            g->part_rows.assign(plan.start, plan.start + parts + 1);
+            for (int r = 1; r < parts; r++) g->part_rows[r] &= ~31;
         }
     }
 

@@ -75,6 +75,13 @@ struct rwr_graph {
     int32_t x_blocks = 1;
     int32_t x_block_size = 0;
     int32_t v_rows = 0;                 // rows of this rank (= row_end - row_begin)
+    // slice-aligned compact column blocks of a partitioned graph (stream.cu: overlapped exchange): block k of the stream
+    // holds the links whose source belongs to rank (rank - k) mod P, only the non-empty (row, block) pairs are stored
+    bool ws_compact = false;
+    int32_t v_compact = 0;              // non-empty (row, block) pairs == virtual rows of the stream
+    DevBuf<u32> vbits, vbase;           // [x_blocks][ceil(v_rows / 32)] presence bitmap and compact index of a word's first pair
+    int32_t vwords = 0;
+    int32_t blk_first_tile[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tile that holds the first link of stream block k
     DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
     DevBuf<u8> node_type_int;
     DevBuf<int32_t> items_by_id_desc;   // lazily: internal indices of ITEM nodes, id descending (full ranking)
@@ -93,6 +100,8 @@ struct rwr_graph {
     int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
     std::vector<int> part_rows;           // [n_ranks + 1] first row of every rank's slice
     std::vector<int> part_hot;            // [n_ranks] hot (degree-sorted, dealt one by one) nodes at the head of every slice
+    std::vector<int> deal_rows;           // [n_ranks + 1] first label the deal gave to every slice; part_rows is deal_rows rounded
+                                          // down to a multiple of 32 (a 128-byte line of x never spans two owners)
     // hub table of a partitioned graph: the part_hub_seg hottest labels of every slice, slice after slice; the edge stream
     // stores hub sources as their table slot and every other source as label + part_hub (stream.cu: HubMap)
     int32_t part_hub = 0, part_hub_seg = 0;
@@ -101,6 +110,15 @@ struct rwr_graph {
     bool p2p = false;
     void* px[2] = {nullptr, nullptr};     // (n + 8) * 8 bytes each, cudaMalloc
     std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
+    // overlapped exchange (dist.cu): every rank's slice of the next x travels to the peers by the copy engines on
+    // `xstream` while the next SpMV already runs; psync is the peer-mapped page of arrival tags
+    bool overlap = false;
+    void* psync = nullptr;                // DistSync, cudaMalloc, mapped by every peer
+    std::vector<void*> peer_psync;        // [n_ranks]
+    cudaStream_t xstream = nullptr;
+    cudaEvent_t ev_fin = nullptr, ev_push[2] = {nullptr, nullptr};
+    bool push_pending[2] = {false, false};
+    uint64_t xtag = 0;                    // tag of the last slice pushed (monotone over the life of the handle)
 
     // fixed-count runs replay a captured CUDA graph of their n_iter x (k_spmv_ws, k_cutrows_ws, k_finish_ws) launches: small
     // graphs (the reference's ego networks are a few thousand nodes) are launch-bound otherwise.  One per precision.

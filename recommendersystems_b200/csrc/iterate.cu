@@ -26,7 +26,7 @@ __global__ void k_init(int n, int seed, T omc, const T* __restrict__ inv, T* __r
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < 8) { x0[n + j] = (T)0; x1[n + j] = (T)0; }     // x[n] is the always-zero entry the edge stream pads with
     if (j == 0) {
-        ctl->resid = 0.0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0;
+        ctl->resid = 0.0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0; ctl->fault = 0;
         ctl->tile_ctr = 0;
         ctl->seed = seed;
         if (seed < 0) ctl->S = S_uniform;
@@ -129,11 +129,15 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool resid, d
     cudaStream_t st = g->stream;
     const bool parted = dist_n_ranks(g->comm) > 1;
     // on a row slice the convergence test needs the residual of all slices: it runs after the exchange
+    const int b_next = ((const void*)p.x_next == g->px[0]) ? 0 : 1;
+    if (g->overlap) dist_before_iteration(g, b_next);        // the copy engines are done with the vector this iteration overwrites
     ws_launch_iteration<T>(g, p, resid, thr, parted ? 0 : use_thr);
     static const bool skip_exchange = getenv("RWR_DIST_SKIP") != nullptr;      // timing probe only: wrong results
     if (parted && !skip_exchange) {
-        // x_next: already in every peer's copy when the epilogue stored it there (p.n_peers > 0), else NCCL
-        dist_exchange(g, p.n_peers ? nullptr : p.x_next, sizeof(T), p.ctl->red);
+        // x_next: pushed by the copy engines while the next SpMV runs (overlapped exchange), or already in every peer's copy
+        // when the epilogue stored it there (p.n_peers > 0), else NCCL
+        if (g->overlap) dist_push_slice(g, b_next, sizeof(T));
+        dist_exchange(g, (p.n_peers || g->overlap) ? nullptr : p.x_next, sizeof(T), p.ctl->red);
         k_after_reduce<<<1, 1, 0, st>>>(p.ctl, thr, use_thr);
         KERNEL_CHECK();
     }
@@ -151,7 +155,8 @@ struct RunWorkspace {
     }
     // column blocking of x (experimental): partial row sums of the virtual rows
     void alloc_yv(rwr_graph* g, size_t elt) {
-        if (g->x_blocks > 1) yv.alloc(&g->scratch, (size_t)g->x_blocks * (size_t)g->v_rows * elt + 16);
+        if (g->ws_compact) yv.alloc(&g->scratch, (size_t)g->v_compact * elt + 16);
+        else if (g->x_blocks > 1) yv.alloc(&g->scratch, (size_t)g->x_blocks * (size_t)g->v_rows * elt + 16);
     }
 };
 
@@ -159,7 +164,7 @@ struct RunWorkspace {
 // or -- on a slice of a partitioned graph, whose labels are dealt over the slices -- the hot head of this rank's own rows
 static int hot_limit(const rwr_graph* g) {
     const int parts = dist_n_ranks(g->comm);
-    if (parts > 1 && (int)g->part_hot.size() == parts) return g->row_begin + g->part_hot[dist_rank(g->comm)];
+    if (parts > 1 && (int)g->part_hot.size() == parts) return g->deal_rows[dist_rank(g->comm)] + g->part_hot[dist_rank(g->comm)];
     return g->n_hot;
 }
 
@@ -168,10 +173,27 @@ template <typename T>
 static void set_peers(rwr_graph* g, IterParams<T>& p, const void* x_next) {
     p.parted = dist_n_ranks(g->comm) > 1;
     p.n_peers = 0;
-    if (!g->p2p) return;
+    if (!g->p2p || g->overlap) return;          // overlapped exchange: the copy engines carry the slice, not the epilogue
     const int b = (x_next == g->px[0]) ? 0 : 1, me = dist_rank(g->comm);
     for (int r = 0; r < (int)g->peer_px[b].size(); r++)
         if (r != me) p.peer_next[p.n_peers++] = g->peer_px[b][r];
+}
+
+// Block layout of the stream and the tags of the overlapped exchange for the iteration that writes `x_next`.  `first`: the
+// gather vector of this iteration comes from k_init (every rank computes all of it), nothing is in flight.
+template <typename T>
+static void set_exchange(rwr_graph* g, IterParams<T>& p, const void* x_next, bool first, bool live) {
+    const int P = dist_n_ranks(g->comm), me = dist_rank(g->comm);
+    p.compact = g->ws_compact ? 1 : 0;
+    p.vbits = g->vbits.p; p.vbase = g->vbase.p; p.vwords = g->vwords;
+    for (int k = 0; k < 8; k++) { p.blk_first_tile[k] = g->blk_first_tile[k]; p.blk_src[k] = ((me - k) % P + P) % P; }
+    p.arrive = nullptr; p.wait_tag = 0; p.tag_out = nullptr; p.tag_out_val = 0;
+    if (g->overlap && live) {
+        DistSync* ds = (DistSync*)g->psync;
+        p.tag_out = &ds->tag_out[(x_next == g->px[0]) ? 0 : 1];
+        p.tag_out_val = ++g->xtag;
+        if (!first) { p.arrive = ds->arrive; p.wait_tag = p.tag_out_val - 1; }
+    }
 }
 
 // Runs one seed.  mode 0: fixed n_iter; mode 1: threshold.  Final rank lands in y_out (internal labels).
@@ -218,6 +240,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
             for (int it = 0; it < n_iter; it++) {
                 p.x = x_cur; p.x_next = x_nxt; p.r_prev = nullptr; p.y = y_out;
                 set_peers<T>(g, p, x_nxt);
+                set_exchange<T>(g, p, x_nxt, it == 0, true);
                 launch_iteration<T>(g, p, /*resid=*/false, 0.0, 0);
                 std::swap(x_cur, x_nxt);
             }
@@ -273,6 +296,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
                 T* target = (r_cur == ya) ? y_out : ya;
                 p.x = x_cur; p.x_next = x_nxt; p.r_prev = r_cur; p.y = target;
                 set_peers<T>(g, p, x_nxt);
+                set_exchange<T>(g, p, x_nxt, launched == 0, true);
                 launch_iteration<T>(g, p, /*resid=*/true, thr, 1);
                 std::swap(x_cur, x_nxt);
                 r_cur = target;
@@ -287,13 +311,27 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
         // the rank of iteration h.iters sits in ya when h.iters is even (r0 was in ya), else in y_out
         if ((h.iters & 1) == 0 && n) CUDA_CHECK(cudaMemcpyAsync(y_out, ya, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     }
-    if (launched > 0) dist_allgather_rows(g, y_out, sizeof(T));       // row-partitioned: every rank gets the whole rank vector
+    if (launched > 0) {
+        // every push of this rank is over before it enters the collective that ends the run: once the allGather returns,
+        // no peer is still writing into this rank's gather vectors either
+        dist_drain_pushes(g);
+        dist_allgather_rows(g, y_out, sizeof(T));                     // row-partitioned: every rank gets the whole rank vector
+    }
     CUDA_CHECK(cudaEventRecord(ev1, st));
     if (!iter_ms) return;                          // the caller keeps enqueueing and reads the events after its own sync
     CUDA_CHECK(cudaEventSynchronize(ev1));
     float ms = 0.f;
     CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
     *iter_ms += ms;
+}
+
+// a k_spmv_ws that gave up waiting for a peer's slice leaves a mark: the results of that run are void
+static void check_exchange_fault(rwr_graph* g, const IterCtl* ctl) {
+    if (!g->overlap) return;
+    IterCtl h{};
+    CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
+    CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (h.fault) RWR_FAIL(RWR_E_NCCL, "row-partitioned exchange: a peer's slice of x did not arrive in time (rank out of step or down)");
 }
 
 template <typename T>
@@ -335,6 +373,7 @@ static void run_all(rwr_graph* g, rwr_result* res, const int32_t* seeds, int n_s
     CUDA_CHECK(cudaEventSynchronize(evB));
     CUDA_CHECK(cudaEventElapsedTime(&res->total_ms, evA, evB));
     res->launches = g->pool.launches - launches0;
+    check_exchange_fault(g, ws.ctl.p);
 }
 
 template <typename T>
@@ -377,6 +416,7 @@ static void profile_impl(rwr_graph* g, int seed_orig, double c, int reps, float*
     for (int it = 0; it < 3 + reps; it++) {
         p.x = x_cur; p.x_next = x_nxt;
         set_peers<T>(g, p, x_nxt);
+        set_exchange<T>(g, p, x_nxt, true, false);       // kernel timing only: no pushes, nothing to wait for
         const int r = it - 3;
         if (r >= 0) CUDA_CHECK(cudaEventRecord(ev[3 * r], st));
         ws_launch_spmv_only<T>(g, p);
@@ -416,13 +456,18 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     const int64_t l0 = g->pool.launches;
     int it = 0;
     double rs = 0;
-    if (ext0 && ext1) {
+    if (ext0 && ext1 && !g->overlap) {
         // no host synchronisation: the workspace goes back to the scratch pool while the kernels are still queued, which is
         // safe because every later user of those blocks enqueues on the same stream
         run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, nullptr, ext0, ext1);
     } else {
         DevEvent ev0, ev1;
         run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, iter_ms, ev0, ev1);
+        check_exchange_fault(g, ws.ctl.p);
+        if (ext0 && ext1) {                       // the caller reads its own events: bracket the (finished) run for it
+            CUDA_CHECK(cudaEventRecord(ext0, g->stream));
+            CUDA_CHECK(cudaEventRecord(ext1, g->stream));
+        }
     }
     *launches += g->pool.launches - l0;
 }

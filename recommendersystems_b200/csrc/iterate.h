@@ -13,6 +13,7 @@ struct IterCtl {
                         // launch parameters, so that a captured iteration graph can be replayed for any seed
     unsigned tile_ctr;  // k_spmv_ws: next tile to hand out (reset by k_finish_ws)
     double red[2];     // row-partitioned graphs: this rank's {restart mass, residual} partials, summed over the ranks in place
+    int fault;         // k_spmv_ws gave up waiting for a peer's slice (exchange timeout): the run is void
 };
 
 struct rwr_result {

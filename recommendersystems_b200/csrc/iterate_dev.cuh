@@ -44,6 +44,19 @@ struct IterParams {
     T* yv;
     int x_blocks;
     int v_rows;
+    // compact slice-aligned blocks (partitioned graph, overlapped exchange): only the non-empty (row, block) pairs are
+    // virtual rows; k_finish_ws finds the pair of (row, block k) through a presence bitmap and a per-word prefix count
+    int compact;
+    const u32* vbits;       // [x_blocks][vwords]
+    const u32* vbase;       // [x_blocks][vwords]
+    int vwords;
+    // arrival tags of the peers' slices: k_spmv_ws must not gather from stream block k before arrive[blk_src[k]] >= wait_tag
+    const unsigned long long* arrive;   // [n_ranks], written by the peers' copy engines; null: nothing to wait for
+    unsigned long long wait_tag;
+    int blk_first_tile[8];  // tile holding the first link of stream block k (k = 0: this rank's own rows, never waited for)
+    int blk_src[8];         // rank whose slice stream block k gathers from
+    unsigned long long tag_out_val;     // k_finish_ws: value stored to *tag_out by the last block (tag of the slice just produced)
+    unsigned long long* tag_out;
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

@@ -749,8 +749,6 @@ int rwr_recommend(rwr_graph* g, const int32_t* seeds, int32_t n_seeds, double c,
 // Experiment.cs:121-128 walks the full ranking and, for every test item it meets, adds nHits / (i + 1).  The ranking is a
 // total order (score desc, id desc: Recommender.cs:34-38), so the position of a test item is 1 + the number of candidates
 // that rank before it -- a count, no sort.  One pass over the rank tile Y[n, B] serves all B users of the tile.
-constexpr int EV_GROUP = 8;                      // test items a thread counts for per pass over Y
-
 struct EvalItem {
     u64 key;        // score key of the test item (0 with idx < 0: not a candidate)
     int64_t id;
@@ -793,73 +791,105 @@ __global__ void k_ev_resolve(const int64_t* __restrict__ test_ids, const int* __
     items[i] = it;
 }
 
-// thread (row lane, column): counts, for up to EV_GROUP items of its column, the candidates of its rows that rank before
-template <typename T, int B>
-__global__ void __launch_bounds__(TOPK_THREADS) k_ev_count(const T* __restrict__ y, const u8* __restrict__ type_int,
-                                                           const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
-                                                           size_t words, int n, int cols, const int* __restrict__ iptr, int pass,
-                                                           EvalItem* __restrict__ items) {
-    const int col = threadIdx.x % B, rlane = threadIdx.x / B;
-    constexpr int RPB = TOPK_THREADS / B;
-    if (col >= cols) return;
-    const int first = iptr[col] + pass * EV_GROUP;
-    const int cnt = min(EV_GROUP, iptr[col + 1] - first);
-    if (cnt <= 0) return;
-    u64 tk[EV_GROUP];
-    int64_t tid[EV_GROUP];
-    u32 c[EV_GROUP];
-#pragma unroll
-    for (int g = 0; g < EV_GROUP; g++) {
-        const bool on = g < cnt && items[first + (g < cnt ? g : 0)].idx >= 0;
-        tk[g] = on ? items[first + g].key : ~0ULL;        // nothing ranks before an inactive slot
-        tid[g] = on ? items[first + g].id : INT64_MAX;
-        c[g] = 0;
-    }
-    const u32* ex = excl + (size_t)col * words;
-    for (int j = blockIdx.x * RPB + rlane; j < n; j += gridDim.x * RPB) {
-        if (type_int[j] != RWR_NODE_ITEM) continue;
-        if ((ex[j >> 5] >> (j & 31)) & 1u) continue;
-        const u64 key = score_key((double)y[(size_t)j * B + col]);
-        const int64_t id = id_int[j];
-#pragma unroll
-        for (int g = 0; g < EV_GROUP; g++) c[g] += (key > tk[g]) || (key == tk[g] && id > tid[g]);
-    }
-#pragma unroll
-    for (int g = 0; g < EV_GROUP; g++)
-        if (g < cnt && c[g]) atomicAdd(&items[first + g].before, c[g]);
-}
+// The candidates that rank before a test item are counted with one pass over the rank tile, whatever the number of test
+// items: per column the valid items are sorted ascending by (score key, id); a candidate row finds by binary search how
+// many items it beats (ip = items strictly below it) and adds one to bucket ip of the column's histogram; the number of
+// candidates before sorted item j is then the sum of the buckets above j.
+constexpr int EV_SMEM_ITEMS = 2048;              // tile items whose sorted keys and buckets fit the block's shared memory
 
-// one block per column: positions in ascending order (rank counting), then the reference's loop (Experiment.cs:121-128)
-__global__ void __launch_bounds__(TOPK_THREADS) k_ev_finish(const EvalItem* __restrict__ items, const int* __restrict__ iptr, int k,
-                                                            u32* __restrict__ sorted_pos /* scratch, [items] */,
-                                                            int* __restrict__ hits, double* __restrict__ ap, int* __restrict__ hits_at_k) {
-    const int col = blockIdx.x;
-    const int b = iptr[col], e = iptr[col + 1];
-    __shared__ int n_valid;
-    if (threadIdx.x == 0) n_valid = 0;
+__device__ __forceinline__ bool ev_less(u64 ka, int64_t ia, u64 kb, int64_t ib) { return ka < kb || (ka == kb && ia < ib); }
+
+// one block per column: rank-sort the valid items; sorted[] gets (key, id), sptr[col + 1] the valid count (prefix-summed by
+// the caller's layout: sorted items of column `col` live at [iptr[col], iptr[col] + nvalid[col]))
+__global__ void __launch_bounds__(TOPK_THREADS) k_ev_sort(const EvalItem* __restrict__ items, const int* __restrict__ iptr,
+                                                          u64* __restrict__ skey, int64_t* __restrict__ sid, int* __restrict__ nvalid) {
+    const int col = blockIdx.x, b = iptr[col], e = iptr[col + 1];
+    __shared__ int cnt;
+    if (threadIdx.x == 0) cnt = 0;
     __syncthreads();
     for (int i = b + threadIdx.x; i < e; i += TOPK_THREADS) {
         if (items[i].idx < 0) continue;
-        const u32 pos = items[i].before;
+        const u64 k = items[i].key;
+        const int64_t id = items[i].id;
         int r = 0;
-        for (int j = b; j < e; j++) r += (items[j].idx >= 0) && (items[j].before < pos || (items[j].before == pos && j < i));
-        sorted_pos[b + r] = pos;
-        atomicAdd(&n_valid, 1);
+        for (int j = b; j < e; j++)
+            if (items[j].idx >= 0 && (ev_less(items[j].key, items[j].id, k, id) || (items[j].key == k && items[j].id == id && j < i))) r++;
+        skey[b + r] = k;
+        sid[b + r] = id;
+        atomicAdd(&cnt, 1);
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int nHits = 0, atk = 0;
-        double sumPrecision = 0.0;
-        for (int r = 0; r < n_valid; r++) {
-            const u32 i0 = sorted_pos[b + r];                      // zero-based index in the recommendation list
-            nHits += 1;
-            sumPrecision += (double)nHits / (double)(i0 + 1);       // Experiment.cs:126
-            if ((int)i0 < k) atk++;
-        }
-        hits[col] = nHits;
-        ap[col] = nHits == 0 ? 0.0 : sumPrecision / nHits;          // Experiment.cs:136
-        hits_at_k[col] = atk;
+    if (threadIdx.x == 0) nvalid[col] = cnt;
+}
+
+// thread (row lane, column): bucket of every candidate row.  hist[iptr[col] + col + ip], ip in [0, nvalid[col]]
+template <typename T, int B, bool SMEM>
+__global__ void __launch_bounds__(TOPK_THREADS) k_ev_hist(const T* __restrict__ y, const u8* __restrict__ type_int,
+                                                          const int64_t* __restrict__ id_int, const u32* __restrict__ excl,
+                                                          size_t words, int n, int cols, const int* __restrict__ iptr,
+                                                          const int* __restrict__ nvalid, const u64* __restrict__ skey,
+                                                          const int64_t* __restrict__ sid, u32* __restrict__ hist) {
+    __shared__ u64 s_key[SMEM ? EV_SMEM_ITEMS : 1];
+    __shared__ int64_t s_id[SMEM ? EV_SMEM_ITEMS : 1];
+    __shared__ u32 s_hist[SMEM ? EV_SMEM_ITEMS + TILE_MAXB : 1];
+    const int total = iptr[cols];
+    if (SMEM) {
+        for (int i = threadIdx.x; i < total; i += TOPK_THREADS) { s_key[i] = skey[i]; s_id[i] = sid[i]; }
+        for (int i = threadIdx.x; i < total + cols; i += TOPK_THREADS) s_hist[i] = 0;
+        __syncthreads();
     }
+    const int col = threadIdx.x % B, rlane = threadIdx.x / B;
+    constexpr int RPB = TOPK_THREADS / B;
+    if (col < cols && nvalid[col] > 0) {
+        const int base = iptr[col], m = nvalid[col];
+        const u64* kk = SMEM ? s_key + base : skey + base;
+        const int64_t* ii = SMEM ? s_id + base : sid + base;
+        u32* hh = (SMEM ? s_hist : hist) + base + col;
+        const u32* ex = excl + (size_t)col * words;
+        const u64 kmin = kk[0];
+        for (int j = blockIdx.x * RPB + rlane; j < n; j += gridDim.x * RPB) {
+            if (type_int[j] != RWR_NODE_ITEM) continue;
+            const u64 key = score_key((double)y[(size_t)j * B + col]);
+            if (key < kmin) continue;                                   // beats nothing: bucket 0 is never read
+            if ((ex[j >> 5] >> (j & 31)) & 1u) continue;
+            const int64_t id = id_int[j];
+            int lo = 0, hi = m;                                         // ip = first sorted item that is not below the row
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ev_less(kk[mid], ii[mid], key, id)) lo = mid + 1; else hi = mid;
+            }
+            if (lo > 0) atomicAdd(hh + lo, 1u);
+        }
+    }
+    if (SMEM) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < total + cols; i += TOPK_THREADS)
+            if (s_hist[i]) atomicAdd(hist + i, s_hist[i]);
+    }
+}
+
+// one thread per column: the reference's loop (Experiment.cs:121-128) over the test items in ranking order -- sorted item
+// m-1 comes first -- with position = number of candidates above it
+__global__ void k_ev_finish(const int* __restrict__ iptr, const int* __restrict__ nvalid, const u32* __restrict__ hist, int cols,
+                            int k, int* __restrict__ hits, double* __restrict__ ap, int* __restrict__ hits_at_k) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    const int m = nvalid[col];
+    const u32* hh = hist + iptr[col] + col;
+    int nHits = 0, atk = 0;
+    double sumPrecision = 0.0;
+    u32 above = 0;                                        // candidates that beat sorted item j: buckets j+1 .. m
+    for (int j = m - 1; j >= 0; j--) {
+        above += hh[j + 1];
+        // the (m - 1 - j) test items above j are candidates themselves and are counted in `above` already
+        const u32 i0 = above;                             // zero-based index in the recommendation list
+        nHits += 1;
+        sumPrecision += (double)nHits / (double)(i0 + 1);  // Experiment.cs:126
+        if ((int)i0 < k) atk++;
+    }
+    hits[col] = nHits;
+    ap[col] = nHits == 0 ? 0.0 : sumPrecision / nHits;     // Experiment.cs:136
+    hits_at_k[col] = atk;
 }
 
 static void ensure_id_lookup(rwr_graph* g) {
@@ -913,13 +943,16 @@ static void evaluate_tiles(rwr_graph* g, const int32_t* users, int n_users, cons
     y.alloc(&g->scratch, n * B + 16);
     const size_t words = (n + 31) / 32 + 1;
     const int grid = std::max(1, std::min(std::min(g->sm_count * 4, TOPK_MAX_GRID), (int)div_up(std::max<size_t>(n, 1), TOPK_THREADS)));
-    Scratch<u32> excl_t, sorted_pos;
+    Scratch<u32> excl_t, hist;
     Scratch<EvalItem> items;
-    Scratch<int> d_iptr, no_links, d_hits, d_atk;
+    Scratch<u64> skey;
+    Scratch<int64_t> sid;
+    Scratch<int> d_iptr, no_links, d_hits, d_atk, d_nvalid;
     Scratch<double> d_ap;
     excl_t.alloc(&g->scratch, (size_t)B * words);
-    items.alloc(&g->scratch, (size_t)max_tile_items); sorted_pos.alloc(&g->scratch, (size_t)max_tile_items);
-    d_iptr.alloc(&g->scratch, TILE_MAXB + 1); no_links.alloc(&g->scratch, TILE_MAXB);
+    items.alloc(&g->scratch, (size_t)max_tile_items); hist.alloc(&g->scratch, (size_t)max_tile_items + TILE_MAXB);
+    skey.alloc(&g->scratch, (size_t)max_tile_items); sid.alloc(&g->scratch, (size_t)max_tile_items);
+    d_iptr.alloc(&g->scratch, TILE_MAXB + 1); no_links.alloc(&g->scratch, TILE_MAXB); d_nvalid.alloc(&g->scratch, TILE_MAXB);
     d_hits.alloc(&g->scratch, n_users); d_atk.alloc(&g->scratch, n_users); d_ap.alloc(&g->scratch, n_users);
     DevEvent e0, e1, e2;
     int64_t launches = 0;
@@ -930,32 +963,31 @@ static void evaluate_tiles(rwr_graph* g, const int32_t* users, int n_users, cons
         spmm_run_tile<T>(g, n2o.data() + s0, cnt, c, n_iter, y.p, &launches);
         CUDA_CHECK(cudaEventRecord(e1, st));
         int h_iptr[TILE_MAXB + 1];
-        int max_items = 0;
         for (int j = 0; j <= TILE_MAXB; j++) h_iptr[j] = (int)(test_ptr[s0 + std::min(j, cnt)] - test_ptr[s0]);
-        for (int j = 0; j < cnt; j++) max_items = std::max(max_items, h_iptr[j + 1] - h_iptr[j]);
         const int tile_items = h_iptr[cnt];
         CUDA_CHECK(cudaMemcpyAsync(d_iptr.p, h_iptr, sizeof(h_iptr), cudaMemcpyHostToDevice, st));
         CUDA_CHECK(cudaMemsetAsync(excl_t.p, 0, (size_t)B * words * sizeof(u32), st));
         CUDA_CHECK(cudaMemsetAsync(no_links.p, 0, TILE_MAXB * sizeof(int), st));
         k_mark_excluded_tile<<<dim3(8, cnt), 256, 0, st>>>(g->raw_dst.p, g->raw_type.p, g->raw_ptr.p, d_users.p + s0, g->new_of_old.p,
                                                           g->n, words, excl_t.p, no_links.p);
+        CUDA_CHECK(cudaMemsetAsync(d_nvalid.p, 0, TILE_MAXB * sizeof(int), st));
         if (tile_items) {
             k_ev_resolve<T><<<div_up((size_t)tile_items, 256), 256, 0, st>>>(d_test.p + test_ptr[s0], d_iptr.p, cnt, B, g->ids_sorted.p,
                                                                             g->label_of_sorted.p, g->n, g->node_type_int.p, excl_t.p,
                                                                             words, y.p, items.p);
-            for (int pass = 0; pass * EV_GROUP < max_items; pass++) {
-                if (B == 8)
-                    k_ev_count<T, 8><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
-                                                                   d_iptr.p, pass, items.p);
-                else
-                    k_ev_count<T, 16><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, g->n, cnt,
-                                                                    d_iptr.p, pass, items.p);
-                launches++;
-            }
+            k_ev_sort<<<cnt, TOPK_THREADS, 0, st>>>(items.p, d_iptr.p, skey.p, sid.p, d_nvalid.p);
+            CUDA_CHECK(cudaMemsetAsync(hist.p, 0, ((size_t)tile_items + TILE_MAXB) * sizeof(u32), st));
+            const bool sm = tile_items <= EV_SMEM_ITEMS;
+#define EV_HIST(BB, SM) k_ev_hist<T, BB, SM><<<grid, TOPK_THREADS, 0, st>>>(y.p, g->node_type_int.p, g->node_id_int.p, excl_t.p, words, \
+                                                                            g->n, cnt, d_iptr.p, d_nvalid.p, skey.p, sid.p, hist.p)
+            if (B == 8) { if (sm) EV_HIST(8, true); else EV_HIST(8, false); }
+            else { if (sm) EV_HIST(16, true); else EV_HIST(16, false); }
+#undef EV_HIST
+            launches += 3;
         }
-        k_ev_finish<<<cnt, TOPK_THREADS, 0, st>>>(items.p, d_iptr.p, k, sorted_pos.p, d_hits.p + s0, d_ap.p + s0, d_atk.p + s0);
+        k_ev_finish<<<1, 32, 0, st>>>(d_iptr.p, d_nvalid.p, hist.p, cnt, k, d_hits.p + s0, d_ap.p + s0, d_atk.p + s0);
         KERNEL_CHECK();
-        launches += 3;
+        launches += 2;
         int h_no[TILE_MAXB];
         CUDA_CHECK(cudaMemcpyAsync(h_no, no_links.p, sizeof(h_no), cudaMemcpyDeviceToHost, st));
         CUDA_CHECK(cudaEventRecord(e2, st));

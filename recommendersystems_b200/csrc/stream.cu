@@ -29,6 +29,7 @@
 // row at a tile boundary goes to tail[t] / head[t].  No floating-point atomics anywhere: a run is bit-reproducible; the
 // association of a row sum differs from the reference's sequential one by O(log deg) ulp (all addends >= 0).
 #include <algorithm>
+#include <climits>
 #include <cmath>
 
 #include "iterate_dev.cuh"
@@ -181,6 +182,85 @@ __global__ void k_ws_fill_blocked(const u32* __restrict__ ptr2, const u32* __res
     }
 }
 
+// ---- slice-aligned compact blocks (partitioned graph, overlapped exchange) -------------------------------------------
+// Stream block k of rank r holds the links whose source belongs to rank (r - k) mod P: block 0 gathers from the rank's own
+// slice of x, block k from the slice that arrives k-th (dist.cu: every rank pushes its slice to r+1 first, then r+2, ...).
+// Only the non-empty (row, block) pairs become virtual rows -- no padding links -- and k_finish_ws finds the pair of a
+// row in block k through a presence bitmap and a per-word prefix count.
+struct SliceMap {
+    int parts, rank;
+    int start[9];
+};
+__device__ __forceinline__ int slice_of(const SliceMap& m, u32 label) {
+    int s = 0;
+    for (int r = 1; r < m.parts; r++) s += (label >= (u32)m.start[r]);
+    return s;
+}
+__global__ void k_pair_count(const u32* __restrict__ in_ptr, const int32_t* __restrict__ in_src, int row_begin, int row_end,
+                             u32 lb, u32 le, const SliceMap sm, int R, u32* __restrict__ cnt, u32* __restrict__ keys,
+                             u32* __restrict__ vals) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)(le - lb)) return;
+    const u32 p = lb + (u32)i;
+    int lo = row_begin, hi = row_end;            // in_ptr[lo] <= p < in_ptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (int)(((unsigned)lo + (unsigned)hi) >> 1);
+        if (in_ptr[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int k = (sm.rank - slice_of(sm, (u32)in_src[p]) + sm.parts) % sm.parts;
+    atomicAdd(&cnt[(size_t)k * R + (size_t)(lo - row_begin)], 1u);
+    keys[i] = (u32)k;
+    vals[i] = (u32)i;
+}
+__global__ void k_pair_flags(const u32* __restrict__ cnt, size_t v, u32* __restrict__ flags) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < v) flags[i] = cnt[i] ? 1u : 0u;
+}
+// presence bitmap + compact index of the first pair of every 32-row word; pairs are numbered (block, row)
+__global__ void k_pair_words(const u32* __restrict__ cnt, const u32* __restrict__ cidx, int R, int words, int blocks,
+                             u32* __restrict__ vbits, u32* __restrict__ vbase) {
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t w = t >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= (size_t)words * blocks) return;
+    const int k = (int)(w / words), wi = (int)(w % words);
+    const int row = wi * 32 + lane;
+    const bool on = row < R && cnt[(size_t)k * R + row] != 0;
+    const u32 bits = __ballot_sync(0xffffffffu, on);
+    if (lane == 0) {
+        vbits[w] = bits;
+        vbase[w] = cidx[(size_t)k * R + (size_t)wi * 32];
+    }
+}
+// stream position q -> the pair that owns it (ptr2v has one entry per (block, row) pair, empty pairs repeat their start)
+__global__ void k_ws_fill_compact(const u32* __restrict__ ptr2v, const u32* __restrict__ perm, const int32_t* __restrict__ in_src,
+                                  const double* __restrict__ in_val, int V, int n, u32 nnz2, size_t padded, const HubMap hm,
+                                  int32_t* __restrict__ ws_src, double* __restrict__ ws_val /* may be null */) {
+    const size_t phys = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (phys >= padded) return;
+    const u32 o = (u32)(phys % WS_STAGE);
+    const u32 rnd = o / WS_STEP, ln = (o % WS_STEP) / 4, k = o % 4;
+    const size_t q = phys - o + (size_t)(ln * (WS_R * 4) + rnd * 4 + k);
+    if (q >= nnz2) {
+        ws_src[phys] = (int32_t)((u32)n + (u32)hm.H);
+        if (ws_val) ws_val[phys] = 0.0;
+        return;
+    }
+    const int v = ws_row_of(ptr2v, V, (u32)q);
+    const u32 link = perm[q];                        // perm is in (block, row, accumulation) order == stream order
+    ws_src[phys] = (int32_t)(hub_translate(hm, (u32)in_src[link]) | ((u32)q + 1 == ptr2v[v + 1] ? END_BIT : 0u));
+    if (ws_val) ws_val[phys] = in_val[link];
+}
+__global__ void k_ws_tiles_compact(const u32* __restrict__ ptr2v, const u32* __restrict__ cidx, int V, u32 v_compact, int n_tiles,
+                                   u32 tile_links, u32* __restrict__ ws_tile) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n_tiles) return;
+    if (t == n_tiles) { ws_tile[t] = v_compact; return; }
+    const u32 q = (u32)t * tile_links;
+    const int v = ws_row_of(ptr2v, V, q);
+    ws_tile[t] = cidx[v] | (q > ptr2v[v] ? END_BIT : 0u);
+}
+
 // rwr_opts.x_blocks (0 = auto, 1 = off, 2..64 = forced); the probe knob RWR_X_BLOCKS=<B> overrides it.  Auto is off: a
 // slice of C4 (x = 400 MB) runs at the same L1TEX bound with and without blocking (profiles/r02_c4slice_*), the padding
 // links of the empty virtual rows cost more than the L2 misses they remove.
@@ -278,6 +358,62 @@ void stream_prepare(rwr_graph* g) {
             }
         }
     }
+    // slice-aligned compact blocks: a partitioned graph whose exchange is overlapped with the next SpMV (dist.cu)
+    DevBuf<u32> cidx;
+    g->ws_compact = false;
+    g->v_compact = 0;
+    if (parts > 1 && parts <= 8 && g->x_blocks == 1 && g->v_rows > 0 && dist_overlap_wanted(g)) {
+        const int R = g->v_rows;
+        const size_t V = (size_t)parts * (size_t)R;
+        u32 lim[2] = {0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(&lim[0], g->in_ptr.p + g->row_begin, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&lim[1], g->in_ptr.p + g->row_end, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const u32 lb = lim[0], le = lim[1];
+        const size_t er = (size_t)(le - lb);
+        if (er > 0) {
+            SliceMap smap{};
+            smap.parts = parts;
+            smap.rank = dist_rank(g->comm);
+            for (int r = 0; r <= parts; r++) smap.start[r] = g->part_rows[r];
+            DevBuf<u32> cnt, keys, keys_alt, total_v;
+            cnt.alloc(V + 1); ptr2v.alloc(V + 1); cidx.alloc(V + 1); total_v.alloc(1);
+            keys.alloc(er); keys_alt.alloc(er); perm.alloc(er); perm_alt.alloc(er);
+            CUDA_CHECK(cudaMemsetAsync(cnt.p, 0, (V + 1) * sizeof(u32), st));
+            k_pair_count<<<div_up(er, 256), 256, 0, st>>>(g->in_ptr.p, g->in_src.p, g->row_begin, g->row_end, lb, le, smap, R, cnt.p,
+                                                         keys.p, perm.p);
+            KERNEL_CHECK();
+            prim::exclusive_scan<u32>(cnt.p, ptr2v.p, V, total_v.p, st, &g->pool);
+            CUDA_CHECK(cudaMemcpyAsync(&nnz2, total_v.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(ptr2v.p + V, total_v.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            k_pair_flags<<<div_up(V, 256), 256, 0, st>>>(cnt.p, V, cidx.p);
+            KERNEL_CHECK();
+            prim::exclusive_scan<u32>(cidx.p, cidx.p, V, total_v.p, st, &g->pool);
+            u32 vc = 0;
+            CUDA_CHECK(cudaMemcpyAsync(&vc, total_v.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaMemcpyAsync(cidx.p + V, total_v.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            const bool fl = prim::radix_sort<u32>(keys.p, keys_alt.p, perm.p, perm_alt.p, er, ceil_log2_u64((u64)parts), st, &g->pool);
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            perm_sorted = fl ? perm_alt.p : perm.p;
+            link_base = lb;
+            q0 = 0;
+            g->x_blocks = parts;
+            g->ws_compact = true;
+            g->v_compact = (int32_t)vc;
+            g->vwords = (R + 31) / 32;
+            g->vbits.alloc((size_t)parts * g->vwords, &g->pool);
+            g->vbase.alloc((size_t)parts * g->vwords, &g->pool);
+            k_pair_words<<<div_up((size_t)parts * g->vwords * 32, 256), 256, 0, st>>>(cnt.p, cidx.p, R, g->vwords, parts, g->vbits.p,
+                                                                                     g->vbase.p);
+            KERNEL_CHECK();
+            // first stream position of every block -> the tile that holds it (k_spmv_ws waits for a block's slice there)
+            std::vector<u32> bstart(parts);
+            for (int k = 0; k < parts; k++)
+                CUDA_CHECK(cudaMemcpyAsync(&bstart[k], ptr2v.p + (size_t)k * R, sizeof(u32), cudaMemcpyDeviceToHost, st));
+            CUDA_CHECK(cudaStreamSynchronize(st));
+            for (int k = 0; k < 8; k++) g->blk_first_tile[k] = k < parts ? (int32_t)bstart[k] : INT32_MAX;   // links -> tiles below
+        }
+    }
     const bool blocked = g->x_blocks > 1;
     // hub table of a partitioned graph (see HubMap): the same entry count for both precisions, the FP64 carve-out step
     HubMap hm{};
@@ -291,7 +427,7 @@ void stream_prepare(rwr_graph* g) {
         seg &= ~3L;
         if (seg > 0) {
             hm.parts = parts; hm.seg_len = (int)seg; hm.H = (int)seg * parts;
-            for (int r = 0; r < parts; r++) hm.start[r] = g->part_rows[r];
+            for (int r = 0; r < parts; r++) hm.start[r] = g->deal_rows[r];
             g->part_hub = hm.H;
             g->part_hub_seg = hm.seg_len;
         }
@@ -313,7 +449,17 @@ void stream_prepare(rwr_graph* g) {
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     if (valued) g->ws_val64.alloc(padded, &g->pool);
     g->ws_tile.alloc((size_t)n_tiles + 1, &g->pool);
-    if (blocked) {
+    if (g->ws_compact) {
+        const int V = g->x_blocks * g->v_rows;
+        for (int k = 0; k < 8; k++)
+            if (g->blk_first_tile[k] != INT32_MAX) g->blk_first_tile[k] /= tile_links;
+        if (padded)
+            k_ws_fill_compact<<<div_up(padded, 256), 256, 0, st>>>(ptr2v.p, perm_sorted, g->in_src.p + link_base,
+                                                                  valued ? g->in_val64.p + link_base : nullptr, V, n, nnz2, padded, hm,
+                                                                  g->ws_src.p, valued ? g->ws_val64.p : nullptr);
+        k_ws_tiles_compact<<<div_up((size_t)n_tiles + 1, 256), 256, 0, st>>>(ptr2v.p, cidx.p, V, (u32)g->v_compact, n_tiles,
+                                                                            (u32)tile_links, g->ws_tile.p);
+    } else if (blocked) {
         const int V = g->x_blocks * g->v_rows;
         if (padded)
             k_ws_fill_blocked<<<div_up(padded, 256), 256, 0, st>>>(ptr2v.p, cnt_ptr.p, perm_sorted, g->in_src.p + link_base,
@@ -488,12 +634,13 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
 
 // Warps per CTA: 16 (128 registers each) everywhere but FP32 index-only, whose smaller register footprint lets 20 warps
 // fit without spills (+4.5 % there; 20 warps cost FP64 7 %: more sectors in flight than the L1 side holds).
-template <typename T, bool VALUED> struct WsCfg { static constexpr int WARPS = (sizeof(T) == 4 && !VALUED) ? 20 : WS_WARPS; };
+template <typename T, bool VALUED, bool XWAIT = false> struct WsCfg { static constexpr int WARPS = (sizeof(T) == 4 && !VALUED && !XWAIT) ? 20 : WS_WARPS; };
 
 // DBG: the probe instantiation (rwr_profile_iteration with RWR_DEBUG_MODE) carries the ablation branches; the production
 // instantiation compiles none of them.
-template <typename T, bool VALUED, bool DBG>
-__global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(const IterParams<T> p) {
+// XWAIT: the instantiation for the overlapped exchange of a partitioned graph (waits for the peers' slices block by block).
+template <typename T, bool VALUED, bool DBG, bool XWAIT>
+__global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv_ws(const IterParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (p.ctl->done) return;
     u32 smem0;
@@ -528,12 +675,36 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
     // Tiles are handed out dynamically (one atomic per tile, fetched a whole tile before it is needed): warps that
     // draw cheap tiles (long rows, hub hits) simply take more of them, and the hand-out order keeps the stream walk ascending.
     const int n_tiles = p.ws_tiles;
+    // Overlapped exchange of a partitioned graph: the slices of x this launch gathers from are still arriving (the peers'
+    // copy engines write them, then an arrival tag).  Stream block k may only be touched once the slice of rank blk_src[k]
+    // is complete: a warp checks that when it DRAWS a tile (two tiles before it gathers from it), block after block.
+    int ready = 1;                                 // stream blocks [0, ready) are known to be complete (block 0: own rows)
+    auto wait_for_tile = [&](u32 t) {
+        if (!XWAIT || (int)t >= n_tiles) return;
+        while (ready < p.x_blocks && p.blk_first_tile[ready] <= (int)t) {
+            if (lane == 0) {
+                const unsigned long long* f = p.arrive + p.blk_src[ready];
+                const long long t0 = clock64();
+                unsigned long long v;
+                do {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                    if (v >= p.wait_tag) break;
+                    if (clock64() - t0 > (4LL << 30)) { p.ctl->fault = 1; break; }      // ~2 s: give up, the run is void
+                    __nanosleep(200);
+                } while (true);
+            }
+            __syncwarp();
+            ready++;
+        }
+    };
     u32 grab = 0;                                  // lane 0: the tile drawn most recently (its value is only read a tile later)
     if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
     int cur = (int)__shfl_sync(0xffffffffu, grab, 0);
     if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
     int nxt = (int)__shfl_sync(0xffffffffu, grab, 0);
     if (lane == 0) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+    wait_for_tile((u32)cur);
+    wait_for_tile((u32)nxt);
     // link offset of this lane's first int4 in stage st of tile t (tiles past the end re-read the last one)
     auto pos_of = [&](int t, int st) -> size_t {
         t = t < n_tiles ? t : n_tiles - 1;
@@ -627,6 +798,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED>::WARPS * 32, 1) k_spmv_ws(con
             meta_cur = meta_nxt;
             nxt = (int)__shfl_sync(0xffffffffu, grab, 0);
             if (lane == 0 && nxt < n_tiles) grab = atomicAdd(&p.ctl->tile_ctr, 1u);
+            wait_for_tile((u32)nxt);                      // a whole tile before the first gather from it
             meta_nxt = p.ws_tile[nxt < n_tiles ? nxt : n_tiles];
         }
 #undef WS_HALF
@@ -666,7 +838,9 @@ __global__ void __launch_bounds__(FIX_THREADS) k_cutrows_ws(const IterParams<T> 
 //   restart mass and L1 residual partials; the last block adds the partials in a fixed order -> next S, residual,
 //   iteration count, convergence flag (Model.cs:57-66, :110-115).
 // BLOCKED (column blocking of x, experimental): the raw sum of a row is the sum of its x_blocks virtual rows, block order.
-template <typename T, bool RESID, bool BLOCKED>
+// BMODE 2 (compact slice-aligned blocks): the pair of (row, block k) exists iff bit (row % 32) of vbits[k][row / 32] is set,
+// and is then number vbase[k][row / 32] + popc(lower bits) -- two coalesced words per 32 rows and block.
+template <typename T, bool RESID, int BMODE>
 __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p, double thr, int use_thr) {
     __shared__ double scratch[2 * FIN_THREADS / 32];
     __shared__ int is_last;
@@ -679,17 +853,26 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
     double accS = 0.0, accR = 0.0;
     for (int row = p.row_begin + blockIdx.x * FIN_THREADS + threadIdx.x; row < p.row_end; row += gridDim.x * FIN_THREADS) {
         T y;
-        if (BLOCKED) {
+        if (BMODE == 1) {
             const T* part = p.yv + (row - p.row_begin);
             y = ld_stream(part, pol_first);
             for (int b = 1; b < p.x_blocks; b++) y = add_rn(y, ld_stream(part + (size_t)b * (size_t)p.v_rows, pol_first));
+        } else if (BMODE == 2) {
+            const int i = row - p.row_begin, w = i >> 5;
+            const u32 below = (1u << (i & 31)) - 1u;
+            y = (T)0;
+            for (int b = 0; b < p.x_blocks; b++) {
+                const u32 bits = p.vbits[(size_t)b * p.vwords + w];
+                if ((bits >> (i & 31)) & 1u)
+                    y = add_rn(y, ld_stream(p.yv + p.vbase[(size_t)b * p.vwords + w] + __popc(bits & below), pol_first));
+            }
         } else {
             y = ld_stream(p.y + row, pol_first);
         }
         const T invr = ld_stream(p.inv + row, pol_first);
         if (row == seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
         if (seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
-        if (BLOCKED) p.y[row] = y;
+        if (BMODE != 0) p.y[row] = y;
         const T rw = mul_rn(p.omc, y);
         // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed
         const T xn = mul_rn(rw, invr);
@@ -727,6 +910,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
             ctl->iters += 1;
             ctl->ticket = 0;
             ctl->tile_ctr = 0;                            // the next k_spmv_ws hands its tiles out from the start
+            if (p.tag_out) *p.tag_out = p.tag_out_val;    // the tag the copy engines hand to the peers after this slice
             if (p.parted) {                               // partial sums of this rank's rows: k_after_reduce finishes the job
                 ctl->red[0] = a;
                 ctl->red[1] = b;
@@ -752,9 +936,10 @@ template <typename T>
 void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     const bool valued = g->layout == RWR_LAYOUT_VALUED;
     const size_t smem = (size_t)WS_HDR + (size_t)p.hub * sizeof(T);
-    auto kern = p.debug ? (valued ? k_spmv_ws<T, true, true> : k_spmv_ws<T, false, true>)
-                        : (valued ? k_spmv_ws<T, true, false> : k_spmv_ws<T, false, false>);
-    const int threads = (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS) * 32;
+    auto kern = p.debug ? (valued ? k_spmv_ws<T, true, true, false> : k_spmv_ws<T, false, true, false>)
+                        : p.arrive ? (valued ? k_spmv_ws<T, true, false, true> : k_spmv_ws<T, false, false, true>)
+                                   : (valued ? k_spmv_ws<T, true, false, false> : k_spmv_ws<T, false, false, false>);
+    const int threads = (p.arrive ? WS_WARPS : (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS)) * 32;
     // the opt-in ceiling is a per-function, per-device setting shared by every handle and thread: always the device
     // maximum (a per-launch value would race between threads whose graphs have different hub sizes); the carve-out a
     // launch gets still follows the dynamic size it asks for
@@ -766,7 +951,7 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     if (g->part_hub > 0 && p.hub == g->part_hub) {          // partitioned graph: segmented hub table, shifted gather vector
         pv.hub_segs = (int)g->part_hot.size();
         pv.hub_seg_len = g->part_hub_seg;
-        for (int r = 0; r < pv.hub_segs; r++) pv.hub_start[r] = g->part_rows[r];
+        for (int r = 0; r < pv.hub_segs; r++) pv.hub_start[r] = g->deal_rows[r];
         pv.x = p.x - g->part_hub;
     }
     if (p.x_blocks > 1) pv.y = p.yv;              // the row sums of the virtual rows go to yv
@@ -779,14 +964,19 @@ void ws_launch_finish_only(rwr_graph* g, const IterParams<T>& p, bool resid, dou
         IterParams<T> pv = p;
         pv.y = p.yv;
         k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(pv);
-        if (resid) k_finish_ws<T, true, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
-        else k_finish_ws<T, false, true><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+        if (p.compact) {
+            if (resid) k_finish_ws<T, true, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+            else k_finish_ws<T, false, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+        } else {
+            if (resid) k_finish_ws<T, true, 1><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+            else k_finish_ws<T, false, 1><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+        }
         KERNEL_CHECK();
         return;
     }
     k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(p);
-    if (resid) k_finish_ws<T, true, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
-    else k_finish_ws<T, false, false><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    if (resid) k_finish_ws<T, true, 0><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+    else k_finish_ws<T, false, 0><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
     KERNEL_CHECK();
 }
 template <typename T>

@@ -20,6 +20,7 @@ def main():
     import recommendersystems_b200 as rs
     from recommendersystems_b200.rwr import run_fixed, run_threshold
 
+    mode = sys.argv[1] if len(sys.argv) > 1 else "overlapped"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
@@ -32,11 +33,17 @@ def main():
     for spec, valued in ((dict(seed=11, n_users=3_000, n_items=40_000, n_third=500, authorship_per_mille=700, n_like=150_000,
                                n_friend=30_000, n_follow=2_000, n_mention=0, undefined_per_mille=20, scramble=1, p1_byte=50), False),
                          (dict(seed=12, n_users=2_000, n_items=20_000, n_third=300, authorship_per_mille=700, n_like=80_000,
-                               n_friend=20_000, n_follow=1_000, n_mention=1_500, undefined_per_mille=20, scramble=1, p1_byte=50), True)):
+                               n_friend=20_000, n_follow=1_000, n_mention=1_500, undefined_per_mille=20, scramble=1, p1_byte=50), True),
+                         # ~3.4 M links: every stream block spans many tiles, so the SpMV of the overlapped exchange really
+                         # runs ahead of the slices that are still arriving
+                         (dict(seed=13, n_users=40_000, n_items=360_000, n_third=0, authorship_per_mille=800, n_like=1_400_000,
+                               n_friend=300_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1, p1_byte=61), False)):
         g = rs.Graph.synthetic(spec, comm=comm)
         g.buildGraph()
         info = g.info()
         assert info.n_ranks == world and 0 <= info.row_begin <= info.row_end <= info.n_nodes
+        want_blocks = {"overlapped": world, "peer_stores": 1, "nccl": 1, "peer_stores_blocked": 3}[mode]
+        assert info.x_blocks == want_blocks, (mode, info.x_blocks)
         assert info.layout == (rs._native.LAYOUT_VALUED if valued else rs._native.LAYOUT_INDEX)
         rows = torch.tensor([info.row_end - info.row_begin])
         dist.all_reduce(rows)

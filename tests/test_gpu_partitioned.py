@@ -33,23 +33,21 @@ def test_single_rank_communicator_degenerates_to_the_whole_graph():
     a.close(); b.close(); gp.close(); g.close(); comm.close()
 
 
-def test_two_ranks_match_the_oracle():
+MODES = {
+    "overlapped": {},                                   # default: copy-engine pushes overlapped with the next SpMV
+    "peer_stores": {"RWR_DIST_LEGACY": "1"},           # the epilogue kernel stores the slice into the peers' vectors
+    "nccl": {"RWR_DIST_NO_P2P": "1"},                  # grouped ncclBroadcast of the slices
+    "peer_stores_blocked": {"RWR_DIST_LEGACY": "1", "RWR_X_BLOCKS": "3"},   # padded column blocks on a slice
+}
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+def test_two_ranks_match_the_oracle(mode):
+    """Two ranks, every exchange path, against the CPU oracle (FP64 1e-12, FP32, threshold iteration counts, top-10)."""
     if rs._native.lib().rwr_device_count() < 2:
         pytest.skip("needs two GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29611", os.path.join(ROOT, "tests", "partitioned_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
-    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
-    assert out.stdout.count("PARTITIONED OK") == 2
-
-
-@pytest.mark.xfail(strict=False, reason="experimental column blocking of x on a row slice: not yet run on two GPUs")
-def test_two_ranks_with_column_blocking():
-    """The same worker with RWR_X_BLOCKS=3: every slice's stream is built over 3 x rows virtual rows."""
-    if rs._native.lib().rwr_device_count() < 2:
-        pytest.skip("needs two GPUs")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29613", os.path.join(ROOT, "tests", "partitioned_worker.py")]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, RWR_X_BLOCKS="3"))
+           "--master-port", str(29611 + list(MODES).index(mode)), os.path.join(ROOT, "tests", "partitioned_worker.py"), mode]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=dict(os.environ, **MODES[mode]))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("PARTITIONED OK") == 2
