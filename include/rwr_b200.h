@@ -97,8 +97,8 @@ typedef struct rwr_synth_spec {
 typedef struct rwr_graph_info {
     int32_t n_nodes;
     int32_t built;
-    int64_t n_links_raw;     /* all links handed in (incl. UNDEFINED)                                           */
-    int64_t nnz;             /* explicit links == nnz(W)                                                        */
+    int64_t n_links_raw;     /* all links handed in (incl. UNDEFINED); row-partitioned handle: those this rank holds */
+    int64_t nnz;             /* explicit links == nnz(W) (of the whole graph, also on a row-partitioned handle)   */
     int32_t n_dangling;      /* rows of W without explicit links (Graph.cs:53, :86 `null`)                      */
     int32_t layout;          /* RWR_LAYOUT_VALUED or RWR_LAYOUT_INDEX actually used                             */
     int32_t relabelled;

@@ -13,6 +13,7 @@
 // NCCL is bound at run time (dlopen) so that a single-GPU host needs no NCCL at all.
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "dist.h"
@@ -23,7 +24,7 @@ typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 enum { ncclSuccess = 0 };
 enum { ncclInt8 = 0, ncclChar = 0, ncclFloat64 = 8 };      // nccl.h (2.x): ncclDataType_t
-enum { ncclSum = 0 };
+enum { ncclSum = 0, ncclMax = 2 };
 
 struct NcclApi {
     void* lib = nullptr;
@@ -32,6 +33,8 @@ struct NcclApi {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -57,6 +60,8 @@ void load_nccl() {
     BIND(CommDestroy, "ncclCommDestroy")
     BIND(Broadcast, "ncclBroadcast")
     BIND(AllReduce, "ncclAllReduce")
+    BIND(Send, "ncclSend")
+    BIND(Recv, "ncclRecv")
     BIND(GroupStart, "ncclGroupStart")
     BIND(GroupEnd, "ncclGroupEnd")
     BIND(GetErrorString, "ncclGetErrorString")
@@ -83,6 +88,7 @@ struct rwr_comm {
     bool fake = false;      // RWR_FAKE_COMM probe: a slice of a partitioned graph on one GPU, no exchange (timing only)
 };
 
+bool dist_is_fake(const rwr_comm* c) { return c && c->fake; }
 int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
 int dist_n_ranks(const rwr_comm* c) { return c ? c->n_ranks : 1; }
 
@@ -109,13 +115,45 @@ void dist_exchange(rwr_graph* g, void* x_next, size_t elt, double* two_doubles) 
     NCCL_CHECK(nccl().AllReduce(two_doubles, two_doubles, 2, ncclFloat64, ncclSum, c->comm, g->stream));
 }
 
+void dist_allreduce_sum(rwr_graph* g, void* buf, size_t count, int dtype) {
+    rwr_comm* c = g->comm;
+    if (!c || c->n_ranks < 2 || c->fake || count == 0) return;
+    // NCCL counts are size_t, but keep single calls below 2^31 elements
+    const size_t elt = dtype == DIST_U32 ? 4 : 8, step = (size_t)1 << 30;
+    for (size_t off = 0; off < count; off += step)
+        NCCL_CHECK(nccl().AllReduce((char*)buf + off * elt, (char*)buf + off * elt, std::min(step, count - off), dtype, ncclSum, c->comm, g->stream));
+}
+
+void dist_allreduce_max_u32(rwr_graph* g, u32* buf, size_t count) {
+    rwr_comm* c = g->comm;
+    if (!c || c->n_ranks < 2 || c->fake || count == 0) return;
+    NCCL_CHECK(nccl().AllReduce(buf, buf, count, DIST_U32, ncclMax, c->comm, g->stream));
+}
+
+void dist_alltoallv(rwr_graph* g, const void* send, const size_t* send_off, const size_t* send_cnt, void* recv,
+                    const size_t* recv_off, const size_t* recv_cnt, size_t elt) {
+    rwr_comm* c = g->comm;
+    if (!c || c->fake) return;
+    NcclApi& api = nccl();
+    NCCL_CHECK(api.GroupStart());
+    for (int r = 0; r < c->n_ranks; r++) {
+        if (send_cnt[r]) NCCL_CHECK(api.Send((const char*)send + send_off[r] * elt, send_cnt[r] * elt, ncclInt8, r, c->comm, g->stream));
+        if (recv_cnt[r]) NCCL_CHECK(api.Recv((char*)recv + recv_off[r] * elt, recv_cnt[r] * elt, ncclInt8, r, c->comm, g->stream));
+    }
+    NCCL_CHECK(api.GroupEnd());
+}
+
 void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // synth.cu
 
 // Two persistent gather vectors per rank, mapped by every peer (one process per GPU -> CUDA IPC handles, exchanged
 // through the communicator itself).  RWR_DIST_NO_P2P=1, more than 8 ranks or a failing mapping fall back to NCCL.
 bool dist_overlap_wanted(const rwr_graph* g) {
     const rwr_comm* c = g->comm;
-    return c && c->n_ranks >= 2 && c->n_ranks <= 8 && !getenv("RWR_DIST_LEGACY") && !getenv("RWR_DIST_NO_P2P");
+    if (!c || c->n_ranks < 2 || c->n_ranks > 8 || getenv("RWR_DIST_LEGACY") || getenv("RWR_DIST_NO_P2P")) return false;
+    // two ranks: the one 44-MB-class slice a rank sends rides inside the epilogue kernel almost for free (peer stores at
+    // NVLink rate while the kernel streams its rows), cheaper than the block bookkeeping of the overlapped form
+    // (profiles/r02_slice_probe.txt); from three ranks on the (P - 1)-fold egress would be exposed.  RWR_DIST_OVERLAP=1 forces it.
+    return c->n_ranks >= 3 || getenv("RWR_DIST_OVERLAP") != nullptr;
 }
 
 void dist_setup_p2p(rwr_graph* g) {
@@ -319,7 +357,8 @@ int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t
                           const int32_t* dst, const int32_t* etype, const double* w, const rwr_opts* opts, rwr_comm* comm,
                           rwr_graph** out);                               // graph.cu
 
-// Every rank generates the same graph (the generator is deterministic); rwr_graph_build then keeps this rank's rows.
+// Every rank runs the same deterministic generator and keeps the links of the sources it owns; rwr_graph_build exchanges
+// them so that every rank ends up with the rows of W^T it owns.
 int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opts, rwr_comm* comm, rwr_graph** out) {
     rwr_graph* g = nullptr;
     try {
@@ -331,6 +370,9 @@ int rwr_synth_create_partitioned(const rwr_synth_spec* spec, const rwr_opts* opt
         o.device = comm->device;
         graph_init_device(g, &o);
         g->comm = comm;
+        // every rank generates, sorts and keeps only the links of the sources it owns (the RWR_FAKE_COMM probe and
+        // RWR_PART_REPLICATED=1 keep the whole graph on every rank, as round 1 did)
+        g->part_build = comm->n_ranks > 1 && !comm->fake && !getenv("RWR_PART_REPLICATED");
         AllocStream alloc_on(g->stream);
         synth_generate_device(g, spec);
         *out = g;

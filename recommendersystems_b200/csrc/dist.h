@@ -3,6 +3,7 @@
 
 #include "graph.h"
 
+bool dist_is_fake(const rwr_comm* c);      // RWR_FAKE_COMM probe: one slice on one GPU, no exchange
 int dist_rank(const rwr_comm* c);          // 0 when c is null
 int dist_n_ranks(const rwr_comm* c);       // 1 when c is null
 // After an iteration on a row slice: every rank's x_next slice to all ranks (NCCL, in place; skipped when x_next is
@@ -32,3 +33,12 @@ void dist_push_slice(rwr_graph* g, int b, size_t elt);
 // the main stream waits for every push of this rank still in flight (before a collective that ends a run)
 void dist_drain_pushes(rwr_graph* g);
 void dist_barrier(rwr_graph* g);
+
+// ---- collectives of the partitioned build (graph.cu): in-place sums over the ranks and the all-to-all of the transpose
+enum { DIST_U32 = 3, DIST_I64 = 4, DIST_F64 = 8 };                        // ncclDataType_t values
+void dist_allreduce_sum(rwr_graph* g, void* buf, size_t count, int dtype);
+void dist_allreduce_max_u32(rwr_graph* g, u32* buf, size_t count);
+// rank r sends send_cnt[d] elements (of `elt` bytes) starting at send_off[d] of `send` to every rank d and receives
+// recv_cnt[s] elements from every rank s at recv_off[s] of `recv` (one grouped set of ncclSend / ncclRecv)
+void dist_alltoallv(rwr_graph* g, const void* send, const size_t* send_off, const size_t* send_cnt, void* recv,
+                    const size_t* recv_off, const size_t* recv_cnt, size_t elt);

@@ -211,6 +211,7 @@ extern "C" int rwr_graph_hold_out(rwr_graph* g, const int32_t* users, int32_t n_
     RWR_API_BEGIN
     if (!g || (n_users && !users) || n_users < 0) RWR_FAIL(RWR_E_INVALID, "bad argument");
     if (g->built) RWR_FAIL(RWR_E_ALREADY_BUILT, "hold-out edits `edges`: call it before buildGraph()");
+    if (g->comm) RWR_FAIL(RWR_E_UNSUPPORTED, "hold-out on a row-partitioned handle: evaluate on replicated graphs, users sharded over the ranks");
     if (n_folds < 1 || fold < 0 || fold >= n_folds) RWR_FAIL(RWR_E_INVALID, "fold %d of %d", fold, n_folds);
     for (int i = 0; i < n_users; i++)
         if (users[i] < 0 || users[i] >= g->n) RWR_FAIL(RWR_E_BADSEED, "user %d outside [0, %d)", users[i], g->n);

@@ -33,6 +33,11 @@ __global__ void k_check_src(const int32_t* __restrict__ src, size_t e0, int32_t 
     }
 }
 
+__global__ void k_ptr_diff(const u32* __restrict__ ptr, int32_t n, u32* __restrict__ out) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = ptr[i + 1] - ptr[i];
+}
+
 __global__ void k_iota(u32* out, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = (u32)i;
@@ -119,6 +124,7 @@ struct BuildStats {
 // K4b: longer rows, one warp per row: all-ones rows sum exactly to their length, anything else is summed
 //      sequentially by lane 0 to keep the reference's rounding.
 constexpr u32 ROWSUM_SHORT = 32;
+constexpr size_t WS_PAD_LINKS = 1 << 16;      // head-room of the 32-bit stream offsets (padding links, tile padding)
 
 __device__ __forceinline__ void rowsum_finish(int32_t i, u32 deg, double sum, double w0, bool uniform, double* rowsum,
                                               double* w0norm, u8* uni, BuildStats* st) {
@@ -178,11 +184,31 @@ __global__ void k_normalise(const double* __restrict__ wv, const int32_t* __rest
     if (i < nnz) val[i] = __ddiv_rn(wv[i], rowsum[src_of[i]]);
 }
 
-__global__ void k_degree_keys(const u32* __restrict__ row_ptr, int32_t n, u32 max_out, u32* __restrict__ keys,
+// per-node facts the relabel and the per-node arrays need: explicit out-degree, first out-neighbour (0 without links),
+// common normalised weight (index-only layout) -- of the rows whose links this handle holds; a partitioned build sums the
+// three arrays over the ranks (every node is owned by exactly one rank, the others contribute zeros)
+__global__ void k_node_facts(const u32* __restrict__ row_ptr, const int32_t* __restrict__ col, const double* __restrict__ w0norm,
+                             int32_t n, u32* __restrict__ deg, u32* __restrict__ first_nb, double* __restrict__ w0) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 b = row_ptr[i], d = row_ptr[i + 1] - b;
+    deg[i] = d;
+    first_nb[i] = d ? (u32)col[b] : 0u;
+    w0[i] = d ? w0norm[i] : 0.0;
+}
+__global__ void k_deg_stats(const u32* __restrict__ deg, int32_t n, BuildStats* st) {
+    int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const u32 d = deg[i];
+    if (d == 0) atomicAdd(&st->n_dangling, 1);
+    atomicMax(&st->max_out, d);
+}
+
+__global__ void k_degree_keys(const u32* __restrict__ deg, int32_t n, u32 max_out, u32* __restrict__ keys,
                               u32* __restrict__ vals) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) {
-        keys[i] = max_out - (row_ptr[i + 1] - row_ptr[i]);
+        keys[i] = max_out - deg[i];
         vals[i] = (u32)i;
     }
 }
@@ -198,10 +224,10 @@ __global__ void k_invert_perm(const u32* __restrict__ old_of_new_u, int32_t n, i
 }
 
 // cold == 1 <= out-degree < hot_min.  counts[0] = hot nodes, counts[1] = cold nodes
-__global__ void k_cold_flags(const u32* __restrict__ row_ptr, int32_t n, u32 hot_min, u32* __restrict__ flags, u32* counts) {
+__global__ void k_cold_flags(const u32* __restrict__ degs, int32_t n, u32 hot_min, u32* __restrict__ flags, u32* counts) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u32 deg = row_ptr[i + 1] - row_ptr[i];
+    const u32 deg = degs[i];
     const u32 cold = deg >= 1 && deg < hot_min;
     flags[i] = cold;
     if (deg >= hot_min) atomicAdd(&counts[0], 1u);
@@ -209,14 +235,14 @@ __global__ void k_cold_flags(const u32* __restrict__ row_ptr, int32_t n, u32 hot
 }
 
 // key of a cold node = label of its first out-neighbour when that one is hot, else n_hot + its original index
-__global__ void k_cold_keys(const u32* __restrict__ row_ptr, const int32_t* __restrict__ col,
+__global__ void k_cold_keys(const u32* __restrict__ degs, const u32* __restrict__ first_nb,
                             const int32_t* __restrict__ new_of_old, int32_t n, u32 hot_min, u32 n_hot,
                             const u32* __restrict__ pos, u32* __restrict__ keys, u32* __restrict__ vals) {
     int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const u32 b = row_ptr[i], deg = row_ptr[i + 1] - b;
+    const u32 deg = degs[i];
     if (deg >= 1 && deg < hot_min) {
-        const int32_t nb = col[b];
+        const int32_t nb = (int32_t)first_nb[i];
         const u32 lab = (u32)new_of_old[nb];
         keys[pos[i]] = lab < n_hot ? lab : n_hot + (u32)nb;
         vals[pos[i]] = (u32)i;
@@ -287,8 +313,48 @@ __global__ void k_fill_pull(const u32* __restrict__ order, const int32_t* __rest
     }
 }
 
-__global__ void k_node_arrays(const int32_t* __restrict__ old_of_new, const u32* __restrict__ row_ptr,
-                              const double* __restrict__ w0norm, const u8* __restrict__ uni,
+// ---- transpose of a partitioned build: every local link travels to the rank that owns its target row
+__global__ void k_dest_keys(const int32_t* __restrict__ col, const int32_t* __restrict__ new_of_old, size_t nnz, int parts,
+                            const int* __restrict__ part_rows, u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ cnt) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nnz) return;
+    const int lab = new_of_old[col[i]];
+    int d = 0;
+    for (int r = 1; r < parts; r++) d += (lab >= part_rows[r]);
+    keys[i] = (u32)d;
+    vals[i] = (u32)i;
+    atomicAdd(&cnt[d], 1u);
+}
+// send buffers in destination order: (target label, original source id) [+ normalised weight]
+__global__ void k_pack_links(const u32* __restrict__ order, const int32_t* __restrict__ col, const int32_t* __restrict__ src_of,
+                             const int32_t* __restrict__ new_of_old, const double* __restrict__ val, size_t nnz,
+                             uint2* __restrict__ out, double* __restrict__ out_val /* may be null */) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nnz) return;
+    const u32 e = order[p];
+    out[p] = make_uint2((u32)new_of_old[col[e]], (u32)src_of[e]);
+    if (out_val) out_val[p] = val[e];
+}
+__global__ void k_pair_field(const uint2* __restrict__ pairs, const u32* __restrict__ idx /* may be null */, size_t n, int field,
+                             u32* __restrict__ out, u32* __restrict__ iota /* may be null */) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 v = pairs[idx ? idx[i] : i];
+    out[i] = field ? v.y : v.x;
+    if (iota) iota[i] = (u32)i;
+}
+__global__ void k_fill_pull_recv(const u32* __restrict__ order, const uint2* __restrict__ pairs, const double* __restrict__ vals,
+                                 const int32_t* __restrict__ new_of_old, size_t m, int32_t* __restrict__ in_src,
+                                 double* __restrict__ in_val /* may be null */) {
+    size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= m) return;
+    const u32 e = order[p];
+    in_src[p] = new_of_old[pairs[e].y];
+    if (in_val) in_val[p] = vals[e];
+}
+
+__global__ void k_node_arrays(const int32_t* __restrict__ old_of_new, const u32* __restrict__ degs,
+                              const double* __restrict__ w0,
                               const int64_t* __restrict__ node_id, const u8* __restrict__ node_type, int32_t n,
                               int index_layout, const u32* __restrict__ in_ptr, double* __restrict__ inv_orig,
                               double* __restrict__ inv_int, int64_t* __restrict__ id_int, u8* __restrict__ type_int,
@@ -296,9 +362,8 @@ __global__ void k_node_arrays(const int32_t* __restrict__ old_of_new, const u32*
     int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     int32_t o = old_of_new[j];
-    u32 deg = row_ptr[o + 1] - row_ptr[o];
-    double inv = (deg == 0) ? 0.0 : (index_layout ? w0norm[o] : 1.0);
-    (void)uni;
+    u32 deg = degs[o];
+    double inv = (deg == 0) ? 0.0 : (index_layout ? w0[o] : 1.0);
     inv_orig[o] = inv;
     inv_int[j] = inv;
     id_int[j] = node_id[o];
@@ -488,8 +553,51 @@ static void graph_build_impl(rwr_graph* g) {
         k_normalise<<<grid_for(nnz), 256, 0, st>>>(wv, g->src_of, rowsum.p, nnz, g->val.p);
         KERNEL_CHECK();
     }
-    CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
-    CUDA_CHECK(cudaStreamSynchronize(st));
+    // per-node facts (degree, first neighbour, common weight) of the rows this handle holds; a partitioned build makes them
+    // global: every node is owned by one rank, the others add zeros
+    const bool pb = g->part_build;
+    DevBuf<u32> deg, first_nb;
+    DevBuf<double> w0;
+    deg.alloc((size_t)n + 1); first_nb.alloc((size_t)n + 1); w0.alloc((size_t)n + 1);
+    if (n) {
+        k_node_facts<<<grid_for(n), 256, 0, st>>>(g->row_ptr, g->col, w0norm.p, n, deg.p, first_nb.p, w0.p);
+        KERNEL_CHECK();
+    }
+    if (pb) {
+        // deg[n] carries "this rank saw a row with unequal weights"
+        const u32 nonuni = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        const u32 flag = hs.all_uniform ? 0u : 1u;
+        (void)nonuni;
+        CUDA_CHECK(cudaMemcpyAsync(deg.p + n, &flag, sizeof(u32), cudaMemcpyHostToDevice, st));
+        dist_allreduce_sum(g, deg.p, (size_t)n + 1, DIST_U32);
+        dist_allreduce_sum(g, first_nb.p, (size_t)n, DIST_U32);
+        dist_allreduce_sum(g, w0.p, (size_t)n, DIST_F64);
+        BuildStats z = {0, 1, 0, 0, 0};
+        CUDA_CHECK(cudaMemcpyAsync(stats.p, &z, sizeof(z), cudaMemcpyHostToDevice, st));
+        if (n) k_deg_stats<<<grid_for(n), 256, 0, st>>>(deg.p, n, stats.p);
+        KERNEL_CHECK();
+        u32 any_nonuni = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&any_nonuni, deg.p + n, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        hs.all_uniform = any_nonuni ? 0 : 1;
+        int64_t counts[2] = {(int64_t)nnz, (int64_t)e0};
+        DevBuf<int64_t> dc;
+        dc.alloc(2);
+        CUDA_CHECK(cudaMemcpyAsync(dc.p, counts, sizeof(counts), cudaMemcpyHostToDevice, st));
+        dist_allreduce_sum(g, dc.p, 2, DIST_I64);
+        CUDA_CHECK(cudaMemcpyAsync(counts, dc.p, sizeof(counts), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        g->nnz_global = counts[0];
+        g->e0_global = counts[1];
+        g->deg_all.alloc(n, &g->pool);
+        if (n) CUDA_CHECK(cudaMemcpyAsync(g->deg_all.p, deg.p, (size_t)n * sizeof(u32), cudaMemcpyDeviceToDevice, st));
+    } else {
+        CUDA_CHECK(cudaMemcpyAsync(&hs, stats.p, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+    }
     wv_own.release();
     g->n_dangling = hs.n_dangling;
     g->all_uniform = hs.all_uniform != 0;
@@ -513,7 +621,7 @@ static void graph_build_impl(rwr_graph* g) {
     if (g->relabelled) {
         DevBuf<u32> k0, k1, v0, v1;
         k0.alloc(n); k1.alloc(n); v0.alloc(n); v1.alloc(n);
-        k_degree_keys<<<grid_for(n), 256, 0, st>>>(g->row_ptr, n, hs.max_out, k0.p, v0.p);
+        k_degree_keys<<<grid_for(n), 256, 0, st>>>(deg.p, n, hs.max_out, k0.p, v0.p);
         KERNEL_CHECK();
         bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, n, ceil_log2_u64((u64)hs.max_out + 1), st, &g->pool);
         k_invert_perm<<<grid_for(n), 256, 0, st>>>(fl ? v1.p : v0.p, n, g->old_of_new.p, g->new_of_old.p);
@@ -523,7 +631,7 @@ static void graph_build_impl(rwr_graph* g) {
             DevBuf<u32> counts, pos, total;
             counts.alloc(2); pos.alloc(n); total.alloc(1);
             CUDA_CHECK(cudaMemsetAsync(counts.p, 0, 2 * sizeof(u32), st));
-            k_cold_flags<<<grid_for(n), 256, 0, st>>>(g->row_ptr, n, hot_min, pos.p, counts.p);
+            k_cold_flags<<<grid_for(n), 256, 0, st>>>(deg.p, n, hot_min, pos.p, counts.p);
             KERNEL_CHECK();
             prim::exclusive_scan<u32>(pos.p, pos.p, n, total.p, st, &g->pool);
             u32 hc[2] = {0, 0}, n_cold = 0;
@@ -535,7 +643,7 @@ static void graph_build_impl(rwr_graph* g) {
             if (n_cold) {
                 DevBuf<u32> ck0, ck1, cv0, cv1;
                 ck0.alloc(n_cold); ck1.alloc(n_cold); cv0.alloc(n_cold); cv1.alloc(n_cold);
-                k_cold_keys<<<grid_for(n), 256, 0, st>>>(g->row_ptr, g->col, g->new_of_old.p, n, hot_min, n_hot, pos.p, ck0.p, cv0.p);
+                k_cold_keys<<<grid_for(n), 256, 0, st>>>(deg.p, first_nb.p, g->new_of_old.p, n, hot_min, n_hot, pos.p, ck0.p, cv0.p);
                 KERNEL_CHECK();
                 bool f2 = prim::radix_sort<u32>(ck0.p, ck1.p, cv0.p, cv1.p, n_cold, ceil_log2_u64((u64)n_hot + (u64)n + 1), st, &g->pool);
                 k_assign_cold<<<grid_for(n_cold), 256, 0, st>>>(f2 ? cv1.p : cv0.p, n_cold, n_hot, g->new_of_old.p, g->old_of_new.p);
@@ -585,10 +693,11 @@ static void graph_build_impl(rwr_graph* g) {
 
     // ---- K5: transpose to the pull layout with a stable sort keyed by the (relabelled) target
     g->in_ptr.alloc((size_t)n + 1, &g->pool);
-    g->in_src.alloc(nnz + IDX_PAD, &g->pool);
-    CUDA_CHECK(cudaMemsetAsync(g->in_src.p, 0, (nnz + IDX_PAD) * sizeof(int32_t), st));
-    if (layout == RWR_LAYOUT_VALUED) g->in_val64.alloc(nnz + IDX_PAD, &g->pool);   // k_spmm reads whole groups of 4
-    {
+    if (!pb) {
+        g->nnz_in = (int64_t)nnz;
+        g->in_src.alloc(nnz + IDX_PAD, &g->pool);
+        CUDA_CHECK(cudaMemsetAsync(g->in_src.p, 0, (nnz + IDX_PAD) * sizeof(int32_t), st));
+        if (layout == RWR_LAYOUT_VALUED) g->in_val64.alloc(nnz + IDX_PAD, &g->pool);   // k_spmm reads whole groups of 4
         DevBuf<u32> k0, k1, v0, v1;
         k0.alloc(nnz); k1.alloc(nnz); v0.alloc(nnz); v1.alloc(nnz);
         if (nnz) {
@@ -604,6 +713,94 @@ static void graph_build_impl(rwr_graph* g) {
                                                       layout == RWR_LAYOUT_VALUED ? g->in_val64.p : nullptr);
         KERNEL_CHECK();
         CUDA_CHECK(cudaStreamSynchronize(st));
+    } else {
+        // Partitioned build: this rank holds the links of the SOURCES it owns and needs the links of the TARGET rows it
+        // owns.  Links are bucketed by the rank of their target (one stable 3-bit pass), travel as (target label, original
+        // source id [, weight]) through one grouped all-to-all, and are put into (target, original source, insertion) order
+        // on arrival -- the accumulation order of the reference's push loop (Model.cs:80-88: i ascending).
+        const int parts = dist_n_ranks(g->comm);
+        const bool valued = layout == RWR_LAYOUT_VALUED;
+        DevBuf<int> d_rows;
+        DevBuf<u32> d_cnt;
+        d_rows.alloc(parts + 1); d_cnt.alloc(16);
+        CUDA_CHECK(cudaMemcpyAsync(d_rows.p, g->part_rows.data(), (size_t)(parts + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+        CUDA_CHECK(cudaMemsetAsync(d_cnt.p, 0, 16 * sizeof(u32), st));
+        DevBuf<uint2> send_pairs;
+        DevBuf<double> send_val;
+        send_pairs.alloc(nnz);
+        if (valued) send_val.alloc(nnz);
+        {
+            DevBuf<u32> k0, k1, v0, v1;
+            k0.alloc(nnz); k1.alloc(nnz); v0.alloc(nnz); v1.alloc(nnz);
+            if (nnz) {
+                k_dest_keys<<<grid_for(nnz), 256, 0, st>>>(g->col, g->new_of_old.p, nnz, parts, d_rows.p, k0.p, v0.p, d_cnt.p);
+                KERNEL_CHECK();
+            }
+            const bool fl = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, nnz, std::max(1, ceil_log2_u64((u64)parts)), st, &g->pool);
+            if (nnz) {
+                k_pack_links<<<grid_for(nnz), 256, 0, st>>>(fl ? v1.p : v0.p, g->col, g->src_of, g->new_of_old.p, g->val.p, nnz,
+                                                           send_pairs.p, valued ? send_val.p : nullptr);
+                KERNEL_CHECK();
+            }
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        }
+        // counts matrix: every rank learns how many links it receives from every other rank
+        std::vector<u32> h_send(16, 0);
+        CUDA_CHECK(cudaMemcpyAsync(h_send.data(), d_cnt.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        DevBuf<int64_t> d_mat;
+        d_mat.alloc((size_t)parts * parts);
+        std::vector<int64_t> h_mat((size_t)parts * parts, 0);
+        const int me = dist_rank(g->comm);
+        for (int d = 0; d < parts; d++) h_mat[(size_t)me * parts + d] = (int64_t)h_send[d];
+        CUDA_CHECK(cudaMemcpyAsync(d_mat.p, h_mat.data(), h_mat.size() * sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        dist_allreduce_sum(g, d_mat.p, h_mat.size(), DIST_I64);
+        CUDA_CHECK(cudaMemcpyAsync(h_mat.data(), d_mat.p, h_mat.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        std::vector<size_t> s_off(parts), s_cnt(parts), r_off(parts), r_cnt(parts);
+        size_t so = 0, ro = 0;
+        for (int r = 0; r < parts; r++) {
+            s_off[r] = so; s_cnt[r] = (size_t)h_mat[(size_t)me * parts + r]; so += s_cnt[r];
+            r_off[r] = ro; r_cnt[r] = (size_t)h_mat[(size_t)r * parts + me]; ro += r_cnt[r];
+        }
+        const size_t m = ro;
+        if (m + (size_t)n + WS_PAD_LINKS >= (1ull << 32)) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32 links in one rank's slice");
+        DevBuf<uint2> recv_pairs;
+        DevBuf<double> recv_val;
+        recv_pairs.alloc(m);
+        if (valued) recv_val.alloc(m);
+        dist_alltoallv(g, send_pairs.p, s_off.data(), s_cnt.data(), recv_pairs.p, r_off.data(), r_cnt.data(), sizeof(uint2));
+        if (valued) dist_alltoallv(g, send_val.p, s_off.data(), s_cnt.data(), recv_val.p, r_off.data(), r_cnt.data(), sizeof(double));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        send_pairs.release();
+        send_val.release();
+        // (target label, original source, arrival) order: LSD, source id first, then a stable pass by target
+        g->nnz_in = (int64_t)m;
+        g->in_src.alloc(m + IDX_PAD, &g->pool);
+        CUDA_CHECK(cudaMemsetAsync(g->in_src.p, 0, (m + IDX_PAD) * sizeof(int32_t), st));
+        if (valued) g->in_val64.alloc(m + IDX_PAD, &g->pool);
+        {
+            DevBuf<u32> k0, k1, v0, v1;
+            k0.alloc(m); k1.alloc(m); v0.alloc(m); v1.alloc(m);
+            if (m) k_pair_field<<<grid_for(m), 256, 0, st>>>(recv_pairs.p, nullptr, m, 1, k0.p, v0.p);
+            KERNEL_CHECK();
+            const bool f1 = prim::radix_sort<u32>(k0.p, k1.p, v0.p, v1.p, m, ceil_log2_u64((u64)n), st, &g->pool);
+            u32* ord1 = f1 ? v1.p : v0.p;
+            u32* ord_alt = f1 ? v0.p : v1.p;
+            u32* kk = f1 ? k0.p : k1.p;         // the key buffer that does not hold the sorted keys: reuse for the target keys
+            u32* kk_alt = f1 ? k1.p : k0.p;
+            if (m) k_pair_field<<<grid_for(m), 256, 0, st>>>(recv_pairs.p, ord1, m, 0, kk, nullptr);
+            KERNEL_CHECK();
+            const bool f2 = prim::radix_sort<u32>(kk, kk_alt, ord1, ord_alt, m, ceil_log2_u64((u64)n), st, &g->pool);
+            const u32* sorted = f2 ? kk_alt : kk;
+            const u32* order = f2 ? ord_alt : ord1;
+            k_lower_bounds<u32><<<grid_for((size_t)n + 1), 256, 0, st>>>(sorted, m, n, g->in_ptr.p);
+            if (m)
+                k_fill_pull_recv<<<grid_for(m), 256, 0, st>>>(order, recv_pairs.p, valued ? recv_val.p : nullptr, g->new_of_old.p, m,
+                                                             g->in_src.p, valued ? g->in_val64.p : nullptr);
+            KERNEL_CHECK();
+            CUDA_CHECK(cudaStreamSynchronize(st));
+        }
     }
 
     // ---- per-node arrays in internal labels
@@ -612,7 +809,7 @@ static void graph_build_impl(rwr_graph* g) {
     g->node_id_int.alloc(n, &g->pool);
     g->node_type_int.alloc(n, &g->pool);
     if (n) {
-        k_node_arrays<<<grid_for(n), 256, 0, st>>>(g->old_of_new.p, g->row_ptr, w0norm.p, uni.p, g->node_id.p,
+        k_node_arrays<<<grid_for(n), 256, 0, st>>>(g->old_of_new.p, deg.p, w0.p, g->node_id.p,
                                                    g->node_type.p, n, layout == RWR_LAYOUT_INDEX, g->in_ptr.p,
                                                    g->inv_orig.p, g->inv64.p, g->node_id_int.p, g->node_type_int.p, stats.p);
         KERNEL_CHECK();
@@ -663,6 +860,23 @@ int rwr_graph_create_flat(int32_t n_nodes, const int64_t* node_id, const int32_t
     cudaStream_t st = g->stream;
     AllocStream alloc_on(st);
     g->n = n_nodes;
+    // Partitioned build: every rank is handed the same link list and uploads only the links of the sources it owns
+    // (contiguous pieces of the node range), in their given order
+    std::vector<int32_t> f_src, f_dst, f_et;
+    std::vector<double> f_w;
+    g->part_build = comm && dist_n_ranks(comm) > 1 && !dist_is_fake(comm) && !getenv("RWR_PART_REPLICATED");
+    if (g->part_build) {
+        OwnMap& own = g->own;
+        own.parts = dist_n_ranks(comm); own.rank = dist_rank(comm); own.n_segs = 1;
+        own.seg[0] = 0; own.seg[1] = std::max(1, n_nodes);
+        for (int64_t i = 0; i < n_links; i++) {
+            if (src[i] < 0 || src[i] >= n_nodes) RWR_FAIL(RWR_E_BADINDEX, "link source outside [0, %d)", n_nodes);
+            if (own_rank(own, src[i]) != own.rank) continue;
+            f_src.push_back(src[i]); f_dst.push_back(dst[i]); f_et.push_back(etype[i]); f_w.push_back(w[i]);
+        }
+        n_links = (int64_t)f_src.size();
+        src = f_src.data(); dst = f_dst.data(); etype = f_et.data(); w = f_w.data();
+    }
     g->e0 = n_links;
     const size_t n = (size_t)n_nodes, e0 = (size_t)n_links;
     g->node_id.alloc(n, &g->pool);
@@ -718,8 +932,8 @@ int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info) {
     memset(info, 0, sizeof(*info));
     info->n_nodes = g->n;
     info->built = g->built ? 1 : 0;
-    info->n_links_raw = g->e0;
-    info->nnz = g->built ? g->nnz : 0;
+    info->n_links_raw = g->e0;          // a partitioned build: the links of the sources this rank owns
+    info->nnz = g->built ? (g->part_build ? g->nnz_global : g->nnz) : 0;
     info->n_dangling = g->n_dangling;
     info->layout = g->built ? g->layout : 0;
     info->relabelled = g->relabelled ? 1 : 0;
@@ -819,6 +1033,25 @@ int rwr_graph_get_degrees(rwr_graph* g, int32_t* out_degree, int32_t* raw_degree
     CUDA_CHECK(cudaSetDevice(g->device));
     const size_t n = (size_t)g->n;
     std::vector<u32> rp(n + 1);
+    if (g->part_build) {
+        // every rank holds the links of its own sources only: the per-node counts are summed over the ranks (collective call)
+        AllocStream alloc_on(g->stream);
+        DevBuf<u32> d;
+        d.alloc(n + 1);
+        std::vector<u32> h(n);
+        for (int which = 0; which < 2; which++) {
+            int32_t* out = which ? raw_degree : out_degree;
+            if (!out) continue;
+            if (!which && !g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+            if (n) k_ptr_diff<<<grid_for(n), 256, 0, g->stream>>>(which ? g->raw_ptr.p : g->row_ptr, (int32_t)n, d.p);
+            KERNEL_CHECK();
+            dist_allreduce_sum(g, d.p, n, DIST_U32);
+            CUDA_CHECK(cudaMemcpyAsync(h.data(), d.p, n * 4, cudaMemcpyDeviceToHost, g->stream));
+            CUDA_CHECK(cudaStreamSynchronize(g->stream));
+            for (size_t i = 0; i < n; i++) out[i] = (int32_t)h[i];
+        }
+        return RWR_OK;
+    }
     if (out_degree) {
         if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
         CUDA_CHECK(cudaMemcpyAsync(rp.data(), g->row_ptr, (n + 1) * 4, cudaMemcpyDeviceToHost, g->stream));

@@ -14,6 +14,19 @@ constexpr int IDX_PAD = 8;                                        // ints of sla
 
 struct rwr_comm;
 
+// Partitioned build: which rank holds the raw links of a source node.  The node range is cut into up to three segments
+// (the synthetic generator: users, items, third-party users -- their degrees differ by an order of magnitude, and ids
+// inside a class are scrambled) and every segment is dealt evenly over the ranks in contiguous pieces.
+struct OwnMap {
+    int parts = 1, rank = 0, n_segs = 1;
+    long long seg[5] = {0, 0, 0, 0, 0};       // segment k = [seg[k], seg[k + 1]), none empty
+};
+__host__ __device__ inline int own_rank(const OwnMap& m, long long i) {
+    int k = 0;
+    while (k + 1 < m.n_segs && i >= m.seg[k + 1]) k++;
+    return (int)(((i - m.seg[k]) * m.parts) / (m.seg[k + 1] - m.seg[k]));
+}
+
 struct rwr_graph {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -79,8 +92,7 @@ struct rwr_graph {
     // holds the links whose source belongs to rank (rank - k) mod P, only the non-empty (row, block) pairs are stored
     bool ws_compact = false;
     int32_t v_compact = 0;              // non-empty (row, block) pairs == virtual rows of the stream
-    DevBuf<u32> vbits, vbase;           // [x_blocks][ceil(v_rows / 32)] presence bitmap and compact index of a word's first pair
-    int32_t vwords = 0;
+    DevBuf<u32> vrow_ptr, vpair;        // CSR over the rank's rows: the virtual rows (compact numbers) of a row, block order
     int32_t blk_first_tile[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // tile that holds the first link of stream block k
     DevBuf<int64_t> node_id_int;        // [n] internal labels (top-k)
     DevBuf<u8> node_type_int;
@@ -96,6 +108,14 @@ struct rwr_graph {
     DevBuf<u32> label_of_sorted;
 
     // ---- row-partitioned mode
+    // part_build: every rank holds the raw links and the push CSR of the sources it owns (OwnMap) only; degrees, labels and
+    // per-node arrays are made global with allReduces, the transpose is an all-to-all keyed by the owner of the target row.
+    // false on a partitioned handle only for the RWR_FAKE_COMM probe (one slice cut out of a whole graph on one GPU).
+    bool part_build = false;
+    OwnMap own;
+    int64_t nnz_global = 0, e0_global = 0;  // whole-graph counts of a part_build handle (nnz / e0 are this rank's)
+    int64_t nnz_in = 0;                     // links in the pull arrays (in_src): nnz, or the links received by the transpose
+    DevBuf<u32> deg_all;                    // [n] explicit out-degree of every node (global), part_build only
     rwr_comm* comm = nullptr;
     int32_t row_begin = 0, row_end = 0;   // internal rows of W^T owned by this rank
     std::vector<int> part_rows;           // [n_ranks + 1] first row of every rank's slice

@@ -79,10 +79,10 @@ int hub_entries_for(const rwr_graph* g, int precision) { return ws_hub_entries(g
 
 void iterate_prepare(rwr_graph* g) {
     cudaStream_t st = g->stream;
-    const u64 total = (u64)g->n + (u64)g->nnz;
+    const u64 total = (u64)g->n + (u64)g->nnz_in;
     g->n_chunks = (int)std::max<u64>(1, (total + CHUNK_ITEMS - 1) / CHUNK_ITEMS);
     g->part.alloc((size_t)g->n_chunks + 1, &g->pool);
-    k_partition<<<div_up((size_t)g->n_chunks + 1, 256), 256, 0, st>>>(g->in_ptr.p, g->n, (u32)g->nnz, g->n_chunks, g->part.p);
+    k_partition<<<div_up((size_t)g->n_chunks + 1, 256), 256, 0, st>>>(g->in_ptr.p, g->n, (u32)g->nnz_in, g->n_chunks, g->part.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaStreamSynchronize(st));
     stream_prepare(g);
@@ -96,8 +96,8 @@ void ensure_fp32_arrays(rwr_graph* g) {
         KERNEL_CHECK();
     }
     if (g->layout == RWR_LAYOUT_VALUED && !g->in_val32.p && g->in_val64.p) {     // (a row slice keeps no whole-graph pull arrays)
-        g->in_val32.alloc((size_t)g->nnz + IDX_PAD, &g->pool);
-        if (g->nnz) k_f64_to_f32<<<div_up((size_t)g->nnz, 256), 256, 0, st>>>(g->in_val64.p, g->in_val32.p, (size_t)g->nnz);
+        g->in_val32.alloc((size_t)g->nnz_in + IDX_PAD, &g->pool);
+        if (g->nnz_in) k_f64_to_f32<<<div_up((size_t)g->nnz_in, 256), 256, 0, st>>>(g->in_val64.p, g->in_val32.p, (size_t)g->nnz_in);
         KERNEL_CHECK();
     }
     if (g->layout == RWR_LAYOUT_VALUED && !g->ws_val32.p && g->ws_val64.n) {
@@ -185,7 +185,7 @@ template <typename T>
 static void set_exchange(rwr_graph* g, IterParams<T>& p, const void* x_next, bool first, bool live) {
     const int P = dist_n_ranks(g->comm), me = dist_rank(g->comm);
     p.compact = g->ws_compact ? 1 : 0;
-    p.vbits = g->vbits.p; p.vbase = g->vbase.p; p.vwords = g->vwords;
+    p.vrow_ptr = g->vrow_ptr.p; p.vpair = g->vpair.p;
     for (int k = 0; k < 8; k++) { p.blk_first_tile[k] = g->blk_first_tile[k]; p.blk_src[k] = ((me - k) % P + P) % P; }
     p.arrive = nullptr; p.wait_tag = 0; p.tag_out = nullptr; p.tag_out_val = 0;
     if (g->overlap && live) {

@@ -45,11 +45,10 @@ struct IterParams {
     int x_blocks;
     int v_rows;
     // compact slice-aligned blocks (partitioned graph, overlapped exchange): only the non-empty (row, block) pairs are
-    // virtual rows; k_finish_ws finds the pair of (row, block k) through a presence bitmap and a per-word prefix count
+    // virtual rows; k_finish_ws adds the virtual rows vpair[vrow_ptr[i] .. vrow_ptr[i + 1]) of row i in block order
     int compact;
-    const u32* vbits;       // [x_blocks][vwords]
-    const u32* vbase;       // [x_blocks][vwords]
-    int vwords;
+    const u32* vrow_ptr;    // [v_rows + 1]
+    const u32* vpair;       // [v_compact]
     // arrival tags of the peers' slices: k_spmv_ws must not gather from stream block k before arrive[blk_src[k]] >= wait_tag
     const unsigned long long* arrive;   // [n_ranks], written by the peers' copy engines; null: nothing to wait for
     unsigned long long wait_tag;

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <unordered_set>
 
+#include "dist.h"
 #include "iterate.h"
 #include "primitives.cuh"
 
@@ -387,6 +388,26 @@ static void mark_excluded(rwr_graph* g, int seed, u32* excl, size_t words) {
     if (seed < 0 || seed >= g->n) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
     u32 b, e;
     seed_raw_range(g, seed, &b, &e);
+    if (g->part_build) {
+        // the raw links of the seed live on the rank that owns it: that rank marks the bitmap (and, in the spare last word,
+        // "the seed has links"), the others contribute zeros, one sum over the ranks gives everybody the same bitmap
+        CUDA_CHECK(cudaMemsetAsync(excl, 0, words * sizeof(u32), g->stream));
+        if (e > b) {
+            k_mark_excluded<<<div_up(e - b, 256), 256, 0, g->stream>>>(g->raw_dst.p, g->raw_type.p, b, e, g->new_of_old.p, g->n, excl);
+            KERNEL_CHECK();
+            const u32 one = 1;
+            CUDA_CHECK(cudaMemcpyAsync(excl + words - 1, &one, sizeof(u32), cudaMemcpyHostToDevice, g->stream));
+        }
+        dist_allreduce_sum(g, excl, words, DIST_U32);
+        u32 has = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&has, excl + words - 1, sizeof(u32), cudaMemcpyDeviceToHost, g->stream));
+        CUDA_CHECK(cudaMemsetAsync(excl + words - 1, 0, sizeof(u32), g->stream));
+        CUDA_CHECK(cudaStreamSynchronize(g->stream));
+        if (!has && !g->opts.empty_seed_ok)
+            RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
+        g->pool.launches += 1;
+        return;
+    }
     if (b == e && !g->opts.empty_seed_ok) RWR_FAIL(RWR_E_BADSEED, "seed %d has no `edges` entry (KeyNotFoundException, Recommender.cs:21)", seed);
     CUDA_CHECK(cudaMemsetAsync(excl, 0, words * sizeof(u32), g->stream));
     if (e > b) k_mark_excluded<<<div_up(e - b, 256), 256, 0, g->stream>>>(g->raw_dst.p, g->raw_type.p, b, e, g->new_of_old.p, g->n, excl);

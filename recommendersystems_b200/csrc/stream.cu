@@ -216,21 +216,22 @@ __global__ void k_pair_flags(const u32* __restrict__ cnt, size_t v, u32* __restr
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < v) flags[i] = cnt[i] ? 1u : 0u;
 }
-// presence bitmap + compact index of the first pair of every 32-row word; pairs are numbered (block, row)
-__global__ void k_pair_words(const u32* __restrict__ cnt, const u32* __restrict__ cidx, int R, int words, int blocks,
-                             u32* __restrict__ vbits, u32* __restrict__ vbase) {
-    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t w = t >> 5;
-    const int lane = threadIdx.x & 31;
-    if (w >= (size_t)words * blocks) return;
-    const int k = (int)(w / words), wi = (int)(w % words);
-    const int row = wi * 32 + lane;
-    const bool on = row < R && cnt[(size_t)k * R + row] != 0;
-    const u32 bits = __ballot_sync(0xffffffffu, on);
-    if (lane == 0) {
-        vbits[w] = bits;
-        vbase[w] = cidx[(size_t)k * R + (size_t)wi * 32];
-    }
+// The pairs of a row, in block order, as a CSR over the rows: vrow_ptr[i] .. vrow_ptr[i + 1] index vpair[], which holds the
+// compact (block-major) number of each pair -- what k_finish_ws adds up for row i.
+__global__ void k_pair_row_counts(const u32* __restrict__ cnt, int R, int blocks, u32* __restrict__ per_row) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    u32 c = 0;
+    for (int k = 0; k < blocks; k++) c += cnt[(size_t)k * R + i] != 0;
+    per_row[i] = c;
+}
+__global__ void k_pair_row_fill(const u32* __restrict__ cnt, const u32* __restrict__ cidx, const u32* __restrict__ vrow_ptr, int R,
+                                int blocks, u32* __restrict__ vpair) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    u32 p = vrow_ptr[i];
+    for (int k = 0; k < blocks; k++)
+        if (cnt[(size_t)k * R + i] != 0) vpair[p++] = cidx[(size_t)k * R + i];
 }
 // stream position q -> the pair that owns it (ptr2v has one entry per (block, row) pair, empty pairs repeat their start)
 __global__ void k_ws_fill_compact(const u32* __restrict__ ptr2v, const u32* __restrict__ perm, const int32_t* __restrict__ in_src,
@@ -280,7 +281,7 @@ void stream_prepare(rwr_graph* g) {
         CUDA_CHECK(cudaMemsetAsync(g->ws_tile.p, 0, sizeof(u32), st));
         return;
     }
-    const u64 nnz2_max = (u64)g->nnz + (u64)n;
+    const u64 nnz2_max = (u64)g->nnz_in + (u64)n;
     if (nnz2_max + WS_TILE >= (1ull << 32)) RWR_FAIL(RWR_E_UNSUPPORTED, "edge stream of %llu links exceeds 32-bit offsets", (unsigned long long)nnz2_max);
     DevBuf<u32> ptr2, total;
     ptr2.alloc((size_t)n + 1);
@@ -400,11 +401,13 @@ void stream_prepare(rwr_graph* g) {
             g->x_blocks = parts;
             g->ws_compact = true;
             g->v_compact = (int32_t)vc;
-            g->vwords = (R + 31) / 32;
-            g->vbits.alloc((size_t)parts * g->vwords, &g->pool);
-            g->vbase.alloc((size_t)parts * g->vwords, &g->pool);
-            k_pair_words<<<div_up((size_t)parts * g->vwords * 32, 256), 256, 0, st>>>(cnt.p, cidx.p, R, g->vwords, parts, g->vbits.p,
-                                                                                     g->vbase.p);
+            g->vrow_ptr.alloc((size_t)R + 1, &g->pool);
+            g->vpair.alloc((size_t)vc + 1, &g->pool);
+            k_pair_row_counts<<<div_up((size_t)R, 256), 256, 0, st>>>(cnt.p, R, parts, g->vrow_ptr.p);
+            KERNEL_CHECK();
+            prim::exclusive_scan<u32>(g->vrow_ptr.p, g->vrow_ptr.p, R, total_v.p, st, &g->pool);
+            CUDA_CHECK(cudaMemcpyAsync(g->vrow_ptr.p + R, total_v.p, sizeof(u32), cudaMemcpyDeviceToDevice, st));
+            k_pair_row_fill<<<div_up((size_t)R, 256), 256, 0, st>>>(cnt.p, cidx.p, g->vrow_ptr.p, R, parts, g->vpair.p);
             KERNEL_CHECK();
             // first stream position of every block -> the tile that holds it (k_spmv_ws waits for a block's slice there)
             std::vector<u32> bstart(parts);
@@ -680,7 +683,8 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
     // is complete: a warp checks that when it DRAWS a tile (two tiles before it gathers from it), block after block.
     int ready = 1;                                 // stream blocks [0, ready) are known to be complete (block 0: own rows)
     auto wait_for_tile = [&](u32 t) {
-        if (!XWAIT || (int)t >= n_tiles) return;
+        if constexpr (XWAIT) {
+        if ((int)t >= n_tiles) return;
         while (ready < p.x_blocks && p.blk_first_tile[ready] <= (int)t) {
             if (lane == 0) {
                 const unsigned long long* f = p.arrive + p.blk_src[ready];
@@ -695,6 +699,7 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
             }
             __syncwarp();
             ready++;
+        }
         }
     };
     u32 grab = 0;                                  // lane 0: the tile drawn most recently (its value is only read a tile later)
@@ -838,8 +843,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_cutrows_ws(const IterParams<T> 
 //   restart mass and L1 residual partials; the last block adds the partials in a fixed order -> next S, residual,
 //   iteration count, convergence flag (Model.cs:57-66, :110-115).
 // BLOCKED (column blocking of x, experimental): the raw sum of a row is the sum of its x_blocks virtual rows, block order.
-// BMODE 2 (compact slice-aligned blocks): the pair of (row, block k) exists iff bit (row % 32) of vbits[k][row / 32] is set,
-// and is then number vbase[k][row / 32] + popc(lower bits) -- two coalesced words per 32 rows and block.
+// BMODE 2 (compact slice-aligned blocks): the virtual rows of row i are vpair[vrow_ptr[i] .. vrow_ptr[i + 1]), block order.
 template <typename T, bool RESID, int BMODE>
 __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p, double thr, int use_thr) {
     __shared__ double scratch[2 * FIN_THREADS / 32];
@@ -858,14 +862,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
             y = ld_stream(part, pol_first);
             for (int b = 1; b < p.x_blocks; b++) y = add_rn(y, ld_stream(part + (size_t)b * (size_t)p.v_rows, pol_first));
         } else if (BMODE == 2) {
-            const int i = row - p.row_begin, w = i >> 5;
-            const u32 below = (1u << (i & 31)) - 1u;
+            const int i = row - p.row_begin;
+            const u32 pb = p.vrow_ptr[i], pe = p.vrow_ptr[i + 1];
             y = (T)0;
-            for (int b = 0; b < p.x_blocks; b++) {
-                const u32 bits = p.vbits[(size_t)b * p.vwords + w];
-                if ((bits >> (i & 31)) & 1u)
-                    y = add_rn(y, ld_stream(p.yv + p.vbase[(size_t)b * p.vwords + w] + __popc(bits & below), pol_first));
-            }
+            for (u32 q = pb; q < pe; q++) y = add_rn(y, ld_stream(p.yv + p.vpair[q], pol_first));
         } else {
             y = ld_stream(p.y + row, pol_first);
         }

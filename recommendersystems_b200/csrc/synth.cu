@@ -7,6 +7,9 @@
 //   relation j -> endpoints by per-bit Bernoulli draws on mix64 hashes (R-MAT-style skew), optional scramble;
 //   every relation emits up to two 64-bit keys (src << 31 | class << 28 | dst); sort, unique, drop the sentinel;
 //   canonical "insertion order" of a source = (class: LIKE, FRIENDSHIP, FOLLOW, AUTHORSHIP, MENTION; then target).
+#include <algorithm>
+
+#include "dist.h"
 #include "graph.h"
 #include "primitives.cuh"
 
@@ -51,10 +54,9 @@ __device__ __forceinline__ u64 permU(const SynthDev& s, u64 x) { return s.scramb
 __device__ __forceinline__ u64 permT(const SynthDev& s, u64 x) { return s.scramble ? (x * 2654435761ULL + s.offT) % s.T : x; }
 __device__ __forceinline__ u64 make_key(u64 src, int cls, u64 dst) { return (src << 31) | ((u64)cls << 28) | dst; }
 
-__global__ void k_synth_keys(const SynthDev s, u64* __restrict__ keys) {
-    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= s.nrel) return;
-    u64 k0 = INVALID_KEY, k1 = INVALID_KEY;
+// the (up to) two keys of relation j
+__device__ __forceinline__ void relation_keys(const SynthDev& s, u64 j, u64& k0, u64& k1) {
+    k0 = INVALID_KEY; k1 = INVALID_KEY;
     if (j < s.r_like) {
         if ((hashH(s.seed, j, 15) % 1000) < (u64)s.auth_pm) {
             const u64 a = permU(s, draw(s, j, 0, s.U, s.LU)), it = s.U + j;
@@ -79,8 +81,43 @@ __global__ void k_synth_keys(const SynthDev s, u64* __restrict__ keys) {
         const u64 u = permU(s, draw(s, j, 0, s.U, s.LU)), v = permU(s, draw(s, j, 1, s.U, s.LU));
         if (u != v) k0 = make_key(u, CLS_MENTION, v);
     }
+}
+
+__global__ void k_synth_keys(const SynthDev s, u64* __restrict__ keys) {
+    const u64 j = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= s.nrel) return;
+    u64 k0, k1;
+    relation_keys(s, j, k0, k1);
     keys[2 * j] = k0;
     keys[2 * j + 1] = k1;
+}
+
+// Partitioned build: only the keys whose SOURCE this rank owns.  Pass 1 (keys == null) counts them, pass 2 appends them in
+// any order (the sort that follows makes the order canonical); one atomic per warp.
+__global__ void k_synth_keys_owned(const SynthDev s, const OwnMap own, u64 j0, u64 j1, u64* __restrict__ keys,
+                                   unsigned long long* __restrict__ counter) {
+    const u64 j = j0 + (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 k0 = INVALID_KEY, k1 = INVALID_KEY;
+    if (j < j1) relation_keys(s, j, k0, k1);
+    const bool m0 = k0 != INVALID_KEY && own_rank(own, (long long)(k0 >> 31)) == own.rank;
+    const bool m1 = k1 != INVALID_KEY && own_rank(own, (long long)(k1 >> 31)) == own.rank;
+    const int mine = (int)m0 + (int)m1;
+    const int lane = threadIdx.x & 31;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned long long base = 0;
+    if (lane == 31 && total) base = atomicAdd(counter, (unsigned long long)total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    if (keys) {
+        unsigned long long p = base + (unsigned long long)(incl - mine);
+        if (m0) keys[p++] = k0;
+        if (m1) keys[p] = k1;
+    }
 }
 
 __global__ void k_unique_flags(const u64* __restrict__ keys, size_t n, u32* __restrict__ flags) {
@@ -153,8 +190,21 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec) {
     s.r_follow = s.r_friend + (u64)spec->n_friend;
     s.r_mention = s.r_follow + (u64)spec->n_follow;
     s.nrel = s.r_mention + (u64)spec->n_mention;
-    const size_t slots = (size_t)(2 * s.nrel);
-    if (slots >= (1ULL << 32) - 65536) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 link slots per device");
+    size_t slots = (size_t)(2 * s.nrel);
+    const bool owned = g->part_build;
+    if (owned) {
+        // who holds which source: users, items and third-party users are three populations with very different degrees, so
+        // each of them is dealt evenly over the ranks (ids inside a class carry no locality when `scramble` is on)
+        OwnMap& own = g->own;
+        own.parts = dist_n_ranks(g->comm);
+        own.rank = dist_rank(g->comm);
+        own.n_segs = 0;
+        own.seg[0] = 0;
+        for (u64 len : {s.U, s.T, s.X})
+            if (len) { own.seg[own.n_segs + 1] = own.seg[own.n_segs] + (long long)len; own.n_segs++; }
+    } else if (slots >= (1ULL << 32) - 65536) {
+        RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 link slots per device");
+    }
 
     DevEvent ev0, ev1;
     CUDA_CHECK(cudaEventRecord(ev0, st));
@@ -166,11 +216,34 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec) {
     KERNEL_CHECK();
 
     DevBuf<u64> keys, keys_alt;
-    keys.alloc(slots);
-    keys_alt.alloc(slots);
-    if (s.nrel) {
-        k_synth_keys<<<div_up((size_t)s.nrel, 256), 256, 0, st>>>(s, keys.p);
-        KERNEL_CHECK();
+    if (owned) {
+        DevBuf<unsigned long long> counter;
+        counter.alloc(1);
+        const u64 CH = 1ULL << 30;                        // relations per launch (grid size limit)
+        unsigned long long mine = 0;
+        for (int pass = 0; pass < 2; pass++) {
+            CUDA_CHECK(cudaMemsetAsync(counter.p, 0, sizeof(unsigned long long), st));
+            for (u64 j0 = 0; j0 < s.nrel; j0 += CH) {
+                const u64 j1 = std::min(s.nrel, j0 + CH);
+                k_synth_keys_owned<<<div_up((size_t)(j1 - j0), 256), 256, 0, st>>>(s, g->own, j0, j1, pass ? keys.p : nullptr, counter.p);
+                KERNEL_CHECK();
+            }
+            if (pass == 0) {
+                CUDA_CHECK(cudaMemcpyAsync(&mine, counter.p, sizeof(mine), cudaMemcpyDeviceToHost, st));
+                CUDA_CHECK(cudaStreamSynchronize(st));
+                if (mine >= (1ULL << 32) - 65536) RWR_FAIL(RWR_E_UNSUPPORTED, "more than 2^32-65537 link slots on one rank");
+                slots = (size_t)mine;
+                keys.alloc(slots);
+                keys_alt.alloc(slots);
+            }
+        }
+    } else {
+        keys.alloc(slots);
+        keys_alt.alloc(slots);
+        if (s.nrel) {
+            k_synth_keys<<<div_up((size_t)s.nrel, 256), 256, 0, st>>>(s, keys.p);
+            KERNEL_CHECK();
+        }
     }
     const int end_bit = 31 + ceil_log2_u64(N);
     // the all-ones sentinel must sort last: include every bit when any slot can be invalid

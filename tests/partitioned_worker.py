@@ -38,19 +38,31 @@ def main():
                          # runs ahead of the slices that are still arriving
                          (dict(seed=13, n_users=40_000, n_items=360_000, n_third=0, authorship_per_mille=800, n_like=1_400_000,
                                n_friend=300_000, n_follow=0, n_mention=0, undefined_per_mille=0, scramble=1, p1_byte=61), False)):
-        g = rs.Graph.synthetic(spec, comm=comm)
+        links = O.synth_generate(spec)          # the generator is deterministic: the oracle's CPU copy of the same graph
+        if valued:
+            # the host-array entry point: every rank is handed the whole list and uploads the links of the sources it owns
+            g = rs.Graph.from_arrays(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"], comm=comm)
+        else:
+            g = rs.Graph.synthetic(spec, comm=comm)
         g.buildGraph()
         info = g.info()
         assert info.n_ranks == world and 0 <= info.row_begin <= info.row_end <= info.n_nodes
-        want_blocks = {"overlapped": world, "peer_stores": 1, "nccl": 1, "peer_stores_blocked": 3}[mode]
+        want_blocks = {"overlapped": world, "peer_stores": 1, "nccl": 1, "peer_stores_blocked": 3, "replicated_build": 1}[mode]
         assert info.x_blocks == want_blocks, (mode, info.x_blocks)
         assert info.layout == (rs._native.LAYOUT_VALUED if valued else rs._native.LAYOUT_INDEX)
         rows = torch.tensor([info.row_end - info.row_begin])
         dist.all_reduce(rows)
         assert int(rows) == info.n_nodes, "the slices must cover every row exactly once"
-        links = g.export_links()
+        held = torch.tensor([info.n_links_raw])
+        dist.all_reduce(held)
+        assert int(held) == len(links["src"]) * (world if mode == "replicated_build" else 1)
+        assert np.array_equal(g.degrees(raw=True), np.bincount(links["src"], minlength=info.n_nodes))
         og = O.OracleGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
         assert og.build() == 0
+        assert og.nnz() == info.nnz
+        local = g.export_links()                # a partitioned build keeps the links of the owned sources only
+        if mode != "replicated_build":
+            assert 0 < len(local["src"]) < len(links["src"])
         deg = np.bincount(links["src"], minlength=og.n)
         seeds = [int(np.argmax(deg)), int(np.flatnonzero(deg[:spec["n_users"]] > 3)[5])]
         for seed in seeds:

@@ -34,8 +34,9 @@ def test_single_rank_communicator_degenerates_to_the_whole_graph():
 
 
 MODES = {
-    "overlapped": {},                                   # default: copy-engine pushes overlapped with the next SpMV
-    "peer_stores": {"RWR_DIST_LEGACY": "1"},           # the epilogue kernel stores the slice into the peers' vectors
+    "overlapped": {"RWR_DIST_OVERLAP": "1"},           # copy-engine pushes overlapped with the next SpMV (default from 3 ranks on)
+    "peer_stores": {},                                  # two ranks: the epilogue kernel stores the slice into the peer's vector
+    "replicated_build": {"RWR_PART_REPLICATED": "1"},  # every rank builds the whole graph and keeps its slice (round 1)
     "nccl": {"RWR_DIST_NO_P2P": "1"},                  # grouped ncclBroadcast of the slices
     "peer_stores_blocked": {"RWR_DIST_LEGACY": "1", "RWR_X_BLOCKS": "3"},   # padded column blocks on a slice
 }
