@@ -93,6 +93,12 @@ int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
 int dist_n_ranks(const rwr_comm* c) { return c ? c->n_ranks : 1; }
 
 __global__ void k_dist_noop() {}
+// test knob RWR_DIST_PUSH_DELAY=<microseconds>: holds the copy engines back so that a gather that does not wait for its
+// slice reads stale data for sure (tests/test_gpu_partitioned.py, mode "overlapped_slow")
+__global__ void k_dist_delay(long long cycles) {
+    const long long t0 = clock64();
+    while (clock64() - t0 < cycles) __nanosleep(1000);
+}
 
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
     rwr_comm* c = g->comm;
@@ -219,16 +225,17 @@ void dist_setup_p2p(rwr_graph* g) {
     if (bad != 0.0) { dist_release_p2p(g); return; }
     g->p2p = true;
     if (g->ws_compact && dist_overlap_wanted(g)) {
-        CUDA_CHECK(cudaStreamCreateWithFlags(&g->xstream, cudaStreamNonBlocking));
+        for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaStreamCreateWithFlags(&g->xstream[k], cudaStreamNonBlocking));
         CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fin, cudaEventDisableTiming));
-        for (int b = 0; b < 2; b++) CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_push[b], cudaEventDisableTiming));
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_push[b][k], cudaEventDisableTiming));
         g->overlap = true;
     }
 }
 
 void dist_before_iteration(rwr_graph* g, int b) {
     if (!g->overlap || !g->push_pending[b]) return;
-    CUDA_CHECK(cudaStreamWaitEvent(g->stream, g->ev_push[b], 0));
+    for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaStreamWaitEvent(g->stream, g->ev_push[b][k], 0));
     g->push_pending[b] = false;
 }
 
@@ -239,16 +246,21 @@ void dist_push_slice(rwr_graph* g, int b, size_t elt) {
     const size_t off = (size_t)g->row_begin * elt, len = (size_t)(g->row_end - g->row_begin) * elt;
     DistSync* mine = (DistSync*)g->psync;
     CUDA_CHECK(cudaEventRecord(g->ev_fin, g->stream));
-    CUDA_CHECK(cudaStreamWaitEvent(g->xstream, g->ev_fin, 0));
+    for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaStreamWaitEvent(g->xstream[k], g->ev_fin, 0));
+    static const long long delay_us = getenv("RWR_DIST_PUSH_DELAY") ? atoll(getenv("RWR_DIST_PUSH_DELAY")) : 0;
+    if (delay_us > 0)
+        for (int k = 0; k < rwr_graph::XSTREAMS; k++) k_dist_delay<<<1, 1, 0, g->xstream[k]>>>(delay_us * 1900);
+    // peer me+1 first (it gathers from this slice first), the streams take the peers in turn so that several copy engines
+    // drive the NVLink ports at once
     for (int j = 1; j < P; j++) {
         const int peer = (me + j) % P;
+        cudaStream_t xs = g->xstream[(j - 1) % rwr_graph::XSTREAMS];
         if (len)
-            CUDA_CHECK(cudaMemcpyAsync((unsigned char*)g->peer_px[b][peer] + off, (unsigned char*)g->px[b] + off, len, cudaMemcpyDefault,
-                                       g->xstream));
+            CUDA_CHECK(cudaMemcpyAsync((unsigned char*)g->peer_px[b][peer] + off, (unsigned char*)g->px[b] + off, len, cudaMemcpyDefault, xs));
         DistSync* theirs = (DistSync*)g->peer_psync[peer];
-        CUDA_CHECK(cudaMemcpyAsync(&theirs->arrive[me], &mine->tag_out[b], sizeof(unsigned long long), cudaMemcpyDefault, g->xstream));
+        CUDA_CHECK(cudaMemcpyAsync(&theirs->arrive[me], &mine->tag_out[b], sizeof(unsigned long long), cudaMemcpyDefault, xs));
     }
-    CUDA_CHECK(cudaEventRecord(g->ev_push[b], g->xstream));
+    for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaEventRecord(g->ev_push[b][k], g->xstream[k]));
     g->push_pending[b] = true;
 }
 
@@ -271,9 +283,12 @@ void dist_barrier(rwr_graph* g) {
 // all ranks meet on the communicator, and only then does each rank free the buffers it exported -- cudaFree of memory a
 // peer still has open through cudaIpcOpenMemHandle is undefined behaviour.
 void dist_release_p2p(rwr_graph* g) {
-    if (g->xstream) { cudaStreamSynchronize(g->xstream); cudaStreamDestroy(g->xstream); g->xstream = nullptr; }
+    for (int k = 0; k < rwr_graph::XSTREAMS; k++)
+        if (g->xstream[k]) { cudaStreamSynchronize(g->xstream[k]); cudaStreamDestroy(g->xstream[k]); g->xstream[k] = nullptr; }
     if (g->ev_fin) { cudaEventDestroy(g->ev_fin); g->ev_fin = nullptr; }
-    for (int b = 0; b < 2; b++) if (g->ev_push[b]) { cudaEventDestroy(g->ev_push[b]); g->ev_push[b] = nullptr; }
+    for (int b = 0; b < 2; b++)
+        for (int k = 0; k < rwr_graph::XSTREAMS; k++)
+            if (g->ev_push[b][k]) { cudaEventDestroy(g->ev_push[b][k]); g->ev_push[b][k] = nullptr; }
     g->overlap = false;
     if (!g->px[0] && !g->px[1] && !g->psync && g->peer_px[0].empty() && g->peer_px[1].empty()) { g->p2p = false; return; }
     const int me = dist_rank(g->comm);

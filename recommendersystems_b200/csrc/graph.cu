@@ -8,6 +8,7 @@
 //   K5  pull layout: CSR of W^T (turns the push loop Model.cs:85-88 into a gather), rows and sources relabelled
 //       by descending out-degree, sources inside a row kept in the reference's accumulation order.
 #include <algorithm>
+#include <chrono>
 
 #include "graph.h"
 #include "primitives.cuh"
@@ -317,13 +318,16 @@ __global__ void k_fill_pull(const u32* __restrict__ order, const int32_t* __rest
 __global__ void k_dest_keys(const int32_t* __restrict__ col, const int32_t* __restrict__ new_of_old, size_t nnz, int parts,
                             const int* __restrict__ part_rows, u32* __restrict__ keys, u32* __restrict__ vals, u32* __restrict__ cnt) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nnz) return;
-    const int lab = new_of_old[col[i]];
-    int d = 0;
-    for (int r = 1; r < parts; r++) d += (lab >= part_rows[r]);
-    keys[i] = (u32)d;
-    vals[i] = (u32)i;
-    atomicAdd(&cnt[d], 1u);
+    int d = 64;                                      // lanes past the end: a bucket of their own
+    if (i < nnz) {
+        const int lab = new_of_old[col[i]];
+        d = 0;
+        for (int r = 1; r < parts; r++) d += (lab >= part_rows[r]);
+        keys[i] = (u32)d;
+        vals[i] = (u32)i;
+    }
+    const u32 peers = __match_any_sync(0xffffffffu, d);           // one atomic per bucket and warp
+    if (d < 64 && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&cnt[d], (u32)__popc(peers));
 }
 // send buffers in destination order: (target label, original source id) [+ normalised weight]
 __global__ void k_pack_links(const u32* __restrict__ order, const int32_t* __restrict__ col, const int32_t* __restrict__ src_of,
@@ -463,6 +467,22 @@ void graph_finish_create(rwr_graph* g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
 }
 
+// probe knob RWR_BUILD_TRACE=1: wall time of the build phases on stderr (each mark synchronises the stream)
+struct BuildTrace {
+    bool on = getenv("RWR_BUILD_TRACE") != nullptr;
+    cudaStream_t st;
+    int rank;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    BuildTrace(cudaStream_t s, int r) : st(s), rank(r) {}
+    void mark(const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rwr build r%d] %-28s %8.1f ms\n", rank, what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
+
 void graph_rebuild_raw_ptr(rwr_graph* g) {
     g->raw_ptr.alloc((size_t)g->n + 1, &g->pool);
     k_lower_bounds<int32_t><<<grid_for((size_t)g->n + 1), 256, 0, g->stream>>>(g->raw_src.p, (size_t)g->e0, g->n, g->raw_ptr.p);
@@ -493,6 +513,7 @@ static void graph_build_impl(rwr_graph* g) {
     bad.alloc(1);
     CUDA_CHECK(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
 
+    BuildTrace trace(st, dist_rank(g->comm));
     // ---- K1 + K2: explicit flags, exclusive scan
     DevBuf<u32> pos, total;
     pos.alloc(e0);
@@ -539,6 +560,7 @@ static void graph_build_impl(rwr_graph* g) {
     CUDA_CHECK(cudaStreamSynchronize(st));
     pos.release();
 
+    trace.mark("K1-K3 flags/scan/compact");
     // ---- K4: row sums (sequential order), normalisation
     DevBuf<double> rowsum, w0norm;
     DevBuf<u8> uni;
@@ -553,6 +575,7 @@ static void graph_build_impl(rwr_graph* g) {
         k_normalise<<<grid_for(nnz), 256, 0, st>>>(wv, g->src_of, rowsum.p, nnz, g->val.p);
         KERNEL_CHECK();
     }
+    trace.mark("K4 row sums + normalise");
     // per-node facts (degree, first neighbour, common weight) of the rows this handle holds; a partitioned build makes them
     // global: every node is owned by one rank, the others add zeros
     const bool pb = g->part_build;
@@ -610,6 +633,7 @@ static void graph_build_impl(rwr_graph* g) {
     if (layout != RWR_LAYOUT_INDEX && layout != RWR_LAYOUT_VALUED) RWR_FAIL(RWR_E_INVALID, "unknown layout %d", layout);
     g->layout = layout;
 
+    trace.mark("node facts (+ allReduce)");
     // ---- internal relabel (locality): [hot nodes by descending out-degree == how often x_i is gathered]
     //      ++ [cold nodes (out-degree < hot_min) clustered by their first out-neighbour, original order inside a
     //          cluster: the row of that neighbour then gathers them as one sequential run of x]
@@ -656,6 +680,7 @@ static void graph_build_impl(rwr_graph* g) {
         KERNEL_CHECK();
     }
 
+    trace.mark("relabel");
     // ---- row-partitioned graph: deal the label order over the slices (see k_deal_labels)
     {
         const int parts = dist_n_ranks(g->comm);
@@ -691,6 +716,7 @@ static void graph_build_impl(rwr_graph* g) {
         }
     }
 
+    trace.mark("deal labels");
     // ---- K5: transpose to the pull layout with a stable sort keyed by the (relabelled) target
     g->in_ptr.alloc((size_t)n + 1, &g->pool);
     if (!pb) {
@@ -744,6 +770,7 @@ static void graph_build_impl(rwr_graph* g) {
             }
             CUDA_CHECK(cudaStreamSynchronize(st));
         }
+        trace.mark("K5 bucket by target rank");
         // counts matrix: every rank learns how many links it receives from every other rank
         std::vector<u32> h_send(16, 0);
         CUDA_CHECK(cudaMemcpyAsync(h_send.data(), d_cnt.p, 16 * sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -774,6 +801,7 @@ static void graph_build_impl(rwr_graph* g) {
         CUDA_CHECK(cudaStreamSynchronize(st));
         send_pairs.release();
         send_val.release();
+        trace.mark("K5 all-to-all");
         // (target label, original source, arrival) order: LSD, source id first, then a stable pass by target
         g->nnz_in = (int64_t)m;
         g->in_src.alloc(m + IDX_PAD, &g->pool);
@@ -803,6 +831,7 @@ static void graph_build_impl(rwr_graph* g) {
         }
     }
 
+    trace.mark("K5 sort + pull arrays");
     // ---- per-node arrays in internal labels
     g->inv_orig.alloc(n, &g->pool);
     g->inv64.alloc(n, &g->pool);
@@ -819,8 +848,11 @@ static void graph_build_impl(rwr_graph* g) {
     g->max_in_degree = hs.max_in;
     g->n_items = hs.n_items;
 
+    trace.mark("node arrays");
     iterate_prepare(g);
+    trace.mark("edge stream");
     dist_setup_p2p(g);
+    trace.mark("peer mapping");
 
     CUDA_CHECK(cudaEventRecord(ev.b, st));
     CUDA_CHECK(cudaEventSynchronize(ev.b));

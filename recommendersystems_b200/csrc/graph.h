@@ -135,8 +135,9 @@ struct rwr_graph {
     bool overlap = false;
     void* psync = nullptr;                // DistSync, cudaMalloc, mapped by every peer
     std::vector<void*> peer_psync;        // [n_ranks]
-    cudaStream_t xstream = nullptr;
-    cudaEvent_t ev_fin = nullptr, ev_push[2] = {nullptr, nullptr};
+    static constexpr int XSTREAMS = 3;    // pushes to different peers ride different copy engines
+    cudaStream_t xstream[XSTREAMS] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ev_fin = nullptr, ev_push[2][XSTREAMS] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     bool push_pending[2] = {false, false};
     uint64_t xtag = 0;                    // tag of the last slice pushed (monotone over the life of the handle)
 

@@ -426,7 +426,8 @@ void stream_prepare(rwr_graph* g) {
         long cap = g->opts.hub_entries > 0 ? (long)g->opts.hub_entries : (long)((WS_HUB_AUTO_BYTES - WS_HDR) / 8);
         if ((size_t)g->max_smem_optin > (size_t)WS_HDR) cap = std::min<long>(cap, (long)(((size_t)g->max_smem_optin - WS_HDR) / 8));
         long seg = cap / parts;
-        for (int r = 0; r < parts; r++) seg = std::min<long>(seg, (long)g->part_hot[r]);
+        for (int r = 0; r < parts; r++)                // a segment holds hot labels of ONE owner (ownership is deal_rows rounded to 32)
+            seg = std::min<long>(seg, std::min<long>((long)g->part_hot[r], (long)g->part_rows[r + 1] - (long)g->deal_rows[r]));
         seg &= ~3L;
         if (seg > 0) {
             hm.parts = parts; hm.seg_len = (int)seg; hm.H = (int)seg * parts;
@@ -656,7 +657,20 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
 
     if (threadIdx.x == 0) mbar_init(reinterpret_cast<u64*>(smem_raw), 1);
     __syncthreads();
-    if (p.hub_segs > 0) {                     // partitioned graph: the hottest labels of every slice, segment after segment
+    // partitioned graph: the hub table holds the hottest labels of every slice, segment after segment.  seg_ready[s] (in the
+    // header, after the mbarrier): segment s of the table is loaded.
+    volatile int* seg_ready = reinterpret_cast<volatile int*>(smem_raw + 16);
+    if (p.hub_segs > 0 && XWAIT) {
+        // overlapped exchange: only this rank's own slice of x is complete when the kernel starts.  Its segment is loaded
+        // now; the segment of rank s is loaded by the first warp that finds the slice of s arrived (wait_for_tile below).
+        T* hub = reinterpret_cast<T*>(smem_raw + WS_HDR);
+        const int own = p.blk_src[0];
+        if (threadIdx.x < 8) seg_ready[threadIdx.x] = 0;
+        for (int i = threadIdx.x; i < p.hub_seg_len; i += blockDim.x) hub[own * p.hub_seg_len + i] = p.xhub[p.hub_start[own] + i];
+        __syncthreads();
+        if (threadIdx.x == 0) seg_ready[own] = 1;
+        __syncthreads();
+    } else if (p.hub_segs > 0) {
         T* hub = reinterpret_cast<T*>(smem_raw + WS_HDR);
         for (int i = threadIdx.x; i < p.hub; i += blockDim.x) {
             const int sg = i / p.hub_seg_len;
@@ -698,6 +712,21 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
                 } while (true);
             }
             __syncwarp();
+            if (p.hub_segs > 0) {                           // the slice is here: its hub segment can be loaded (once per CTA,
+                const int sg = p.blk_src[ready];            // a second warp racing here writes the same values)
+                // lane 0 decides for the warp: the flag may flip between the reads of two lanes, and a __syncwarp inside a
+                // branch only some lanes take never completes
+                int need = (lane == 0) ? (seg_ready[sg] == 0) : 0;
+                need = __shfl_sync(0xffffffffu, need, 0);
+                if (need) {
+                    T* hub = reinterpret_cast<T*>(smem_raw + WS_HDR);
+                    for (int i = lane; i < p.hub_seg_len; i += 32) hub[sg * p.hub_seg_len + i] = p.xhub[p.hub_start[sg] + i];
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) seg_ready[sg] = 1;
+                }
+                __threadfence_block();
+            }
             ready++;
         }
         }

@@ -47,7 +47,7 @@ def main():
         g.buildGraph()
         info = g.info()
         assert info.n_ranks == world and 0 <= info.row_begin <= info.row_end <= info.n_nodes
-        want_blocks = {"overlapped": world, "peer_stores": 1, "nccl": 1, "peer_stores_blocked": 3, "replicated_build": 1}[mode]
+        want_blocks = {"overlapped": world, "overlapped_slow": world, "peer_stores": 1, "nccl": 1, "peer_stores_blocked": 3, "replicated_build": 1}[mode]
         assert info.x_blocks == want_blocks, (mode, info.x_blocks)
         assert info.layout == (rs._native.LAYOUT_VALUED if valued else rs._native.LAYOUT_INDEX)
         rows = torch.tensor([info.row_end - info.row_begin])
