@@ -26,10 +26,11 @@ struct DistSync {
     unsigned long long tag_out[2];    // written by k_finish_ws: tag of the slice it just produced in vector b
 };
 bool dist_overlap_wanted(const rwr_graph* g);
+constexpr size_t DIST_PUSH_SMEM_BYTES = 14 * 1024;     // shared memory k_push_slices needs beside k_spmv_ws (3 x 4 KB + reserve)
 // before the iteration that will overwrite vector `b` (0 / 1): the earlier push out of that vector must be over
 void dist_before_iteration(rwr_graph* g, int b);
 // after k_finish_ws produced this rank's slice in vector `b`: push it to every peer, then the tag
-void dist_push_slice(rwr_graph* g, int b, size_t elt);
+void dist_push_slice(rwr_graph* g, int b, size_t elt, unsigned long long tag);
 // the main stream waits for every push of this rank still in flight (before a collective that ends a run)
 void dist_drain_pushes(rwr_graph* g);
 void dist_barrier(rwr_graph* g);

@@ -139,6 +139,9 @@ struct rwr_graph {
     cudaStream_t xstream[XSTREAMS] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev_fin = nullptr, ev_push[2][XSTREAMS] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     bool push_pending[2] = {false, false};
+    int push_streams[2] = {0, 0};
+    unsigned* push_done = nullptr;        // [8] per-peer CTA counters of k_push_slices
+    int xchg_carveout_pct = 0;            // shared-memory carve-out (percent) k_spmv_ws and k_push_slices share on an SM
     uint64_t xtag = 0;                    // tag of the last slice pushed (monotone over the life of the handle)
 
     // fixed-count runs replay a captured CUDA graph of their n_iter x (k_spmv_ws, k_cutrows_ws, k_finish_ws) launches: small

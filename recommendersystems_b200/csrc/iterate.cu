@@ -26,7 +26,7 @@ __global__ void k_init(int n, int seed, T omc, const T* __restrict__ inv, T* __r
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j < 8) { x0[n + j] = (T)0; x1[n + j] = (T)0; }     // x[n] is the always-zero entry the edge stream pads with
     if (j == 0) {
-        ctl->resid = 0.0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0; ctl->fault = 0;
+        ctl->resid = 0.0; ctl->done = 0; ctl->iters = 0; ctl->ticket = 0; ctl->fault = 0; ctl->wait_clk = 0;
         ctl->tile_ctr = 0;
         ctl->seed = seed;
         if (seed < 0) ctl->S = S_uniform;
@@ -136,7 +136,7 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool resid, d
     if (parted && !skip_exchange) {
         // x_next: pushed by the copy engines while the next SpMV runs (overlapped exchange), or already in every peer's copy
         // when the epilogue stored it there (p.n_peers > 0), else NCCL
-        if (g->overlap) dist_push_slice(g, b_next, sizeof(T));
+        if (g->overlap) dist_push_slice(g, b_next, sizeof(T), p.tag_out_val);
         dist_exchange(g, (p.n_peers || g->overlap) ? nullptr : p.x_next, sizeof(T), p.ctl->red);
         k_after_reduce<<<1, 1, 0, st>>>(p.ctl, thr, use_thr);
         KERNEL_CHECK();
@@ -331,6 +331,10 @@ static void check_exchange_fault(rwr_graph* g, const IterCtl* ctl) {
     IterCtl h{};
     CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
+    if (getenv("RWR_XCHG_TRACE"))
+        fprintf(stderr, "[rwr xchg r%d] %d iterations, warps waited %.3f ms in total for slices (%.4f ms per warp and iteration)\n",
+                dist_rank(g->comm), h.iters, (double)h.wait_clk / 1.9e6,
+                h.iters ? (double)h.wait_clk / 1.9e6 / (148.0 * 16.0) / h.iters : 0.0);
     if (h.fault) RWR_FAIL(RWR_E_NCCL, "row-partitioned exchange: a peer's slice of x did not arrive in time (rank out of step or down)");
 }
 

@@ -14,6 +14,7 @@ struct IterCtl {
     unsigned tile_ctr;  // k_spmv_ws: next tile to hand out (reset by k_finish_ws)
     double red[2];     // row-partitioned graphs: this rank's {restart mass, residual} partials, summed over the ranks in place
     int fault;         // k_spmv_ws gave up waiting for a peer's slice (exchange timeout): the run is void
+    unsigned long long wait_clk;   // probe (RWR_XCHG_TRACE): cycles the warps of k_spmv_ws spent waiting for slices, summed
 };
 
 struct rwr_result {

@@ -424,6 +424,8 @@ void stream_prepare(rwr_graph* g) {
     g->part_hub_seg = 0;
     if (parts > 1 && parts <= 8 && g->opts.hub_entries != 0 && (int)g->part_hot.size() == parts && !getenv("RWR_PART_NO_HUB")) {
         long cap = g->opts.hub_entries > 0 ? (long)g->opts.hub_entries : (long)((WS_HUB_AUTO_BYTES - WS_HDR) / 8);
+        // overlapped exchange: k_push_slices lives beside k_spmv_ws on every SM; its buffers come out of the same 100 KB step
+        if (g->ws_compact) cap = std::min<long>(cap, (long)((WS_HUB_AUTO_BYTES - WS_HDR - DIST_PUSH_SMEM_BYTES - 1024) / 8));
         if ((size_t)g->max_smem_optin > (size_t)WS_HDR) cap = std::min<long>(cap, (long)(((size_t)g->max_smem_optin - WS_HDR) / 8));
         long seg = cap / parts;
         for (int r = 0; r < parts; r++)                // a segment holds hot labels of ONE owner (ownership is deal_rows rounded to 32)
@@ -710,6 +712,8 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
                     if (clock64() - t0 > (4LL << 30)) { p.ctl->fault = 1; break; }      // ~2 s: give up, the run is void
                     __nanosleep(200);
                 } while (true);
+                const long long dt = clock64() - t0;
+                if (dt > 2000) atomicAdd(&p.ctl->wait_clk, (unsigned long long)dt);
             }
             __syncwarp();
             if (p.hub_segs > 0) {                           // the slice is here: its hub segment can be loaded (once per CTA,
@@ -984,6 +988,16 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
         pv.x = p.x - g->part_hub;
     }
     if (p.x_blocks > 1) pv.y = p.yv;              // the row sums of the virtual rows go to yv
+    if (g->ws_compact) {
+        // overlapped exchange: the push kernel shares the SM with this one; both ask for the same shared-memory / L1 split
+        // (the smallest step that holds both), or the second CTA would have to wait for an empty SM to change it
+        static const size_t steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+        const size_t need = smem + 1024 + DIST_PUSH_SMEM_BYTES;
+        size_t step = 228;
+        for (size_t s_kb : steps_kb) if (s_kb * 1024 >= need) { step = s_kb; break; }
+        g->xchg_carveout_pct = (int)(step * 100 / 228);
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g->xchg_carveout_pct));
+    }
     kern<<<ws_main_grid(g), threads, smem, g->stream>>>(pv);
     KERNEL_CHECK();
 }
