@@ -93,97 +93,6 @@ int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
 int dist_n_ranks(const rwr_comm* c) { return c ? c->n_ranks : 1; }
 
 __global__ void k_dist_noop() {}
-// The push of the overlapped exchange: this rank's slice of the next x into every peer's gather vector, peer me+1 first,
-// each followed by the arrival tag.  It has to run BESIDE the next k_spmv_ws, whose CTA leaves an SM 4096 registers and a
-// few KB of shared memory, and it has to drive NVLink at full rate: the copy engines reached ~350 GB/s for these
-// peer-mapped buffers (profiles/r02_part8.txt), 128 plain load/store threads per SM are latency-bound.  So one warp per
-// SM lets the TMA do the work: bulk copies global -> shared (mbarrier) and shared -> peer memory (bulk groups), three 4-KB
-// buffers in flight, no registers to speak of.
-constexpr int PUSH_CHUNK = 4096;
-constexpr int PUSH_BUFS = 3;
-constexpr int PUSH_SMEM = PUSH_CHUNK * PUSH_BUFS + 64;
-struct PushArgs {
-    const unsigned char* src;     // this rank's slice in its own vector
-    unsigned char* dst[7];        // the same rows in the peers' vectors, in push order
-    unsigned long long* flag[7];  // arrive[me] on those peers
-    int n_peers;
-    size_t bytes16;               // multiple of 16
-    int n_tail;                   // 4-byte words after that
-    unsigned long long tag;
-    unsigned* done;               // [7] CTAs that have finished a peer
-};
-__device__ __forceinline__ u32 push_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
-__global__ void __launch_bounds__(32, 1) k_push_slices(const PushArgs a) {
-    __shared__ __align__(128) unsigned char buf[PUSH_BUFS][PUSH_CHUNK];
-    __shared__ __align__(8) u64 bar[PUSH_BUFS];
-    const int lane = threadIdx.x;
-    if (lane == 0) {
-        for (int s = 0; s < PUSH_BUFS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(push_smem_addr(&bar[s])));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncwarp();
-    const size_t n_chunks = (a.bytes16 + PUSH_CHUNK - 1) / PUSH_CHUNK;
-    u32 phase[PUSH_BUFS] = {0, 0, 0};
-    for (int j = 0; j < a.n_peers; j++) {
-        if (lane == 0) {
-            unsigned char* d = a.dst[j];
-            // chunks c = blockIdx.x, + gridDim.x, ...; the load of chunk k+1 is issued before the store of chunk k
-            auto chunk_len = [&](size_t c) { return (u32)((c + 1) * PUSH_CHUNK <= a.bytes16 ? PUSH_CHUNK : a.bytes16 - c * PUSH_CHUNK); };
-            auto issue_load = [&](size_t c, int s) {
-                // the bulk store that read buffer s (PUSH_BUFS chunks ago) must be done reading it
-                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PUSH_BUFS - 2) : "memory");
-                const u32 len = chunk_len(c);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(push_smem_addr(&bar[s])), "r"(len) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(push_smem_addr(buf[s])),
-                             "l"(a.src + c * PUSH_CHUNK), "r"(len), "r"(push_smem_addr(&bar[s]))
-                             : "memory");
-            };
-            size_t c = blockIdx.x;
-            int s = 0;
-            if (c < n_chunks) issue_load(c, s);
-            while (c < n_chunks) {
-                const size_t cn = c + gridDim.x;
-                const int sn = (s + 1) % PUSH_BUFS;
-                if (cn < n_chunks) issue_load(cn, sn);
-                // wait for chunk c in buffer s
-                asm volatile(
-                    "{\n.reg .pred p;\nPW:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra PD;\nbra PW;\nPD:\n}\n" ::"r"(push_smem_addr(&bar[s])),
-                    "r"(phase[s])
-                    : "memory");
-                phase[s] ^= 1u;
-                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d + c * PUSH_CHUNK), "r"(push_smem_addr(buf[s])),
-                             "r"(chunk_len(c))
-                             : "memory");
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                c = cn;
-                s = sn;
-            }
-            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every store to this peer has completed
-            asm volatile("fence.proxy.async;" ::: "memory");
-        }
-        if (blockIdx.x == 0 && lane < a.n_tail)
-            reinterpret_cast<unsigned*>(a.dst[j] + a.bytes16)[lane] = reinterpret_cast<const unsigned*>(a.src + a.bytes16)[lane];
-        __threadfence_system();
-        __syncwarp();
-        if (lane == 0) {
-            const unsigned cdone = atomicAdd(&a.done[j], 1u);
-            if (cdone == gridDim.x - 1) {                  // every CTA's stores to this peer are out: hand over the tag
-                a.done[j] = 0;
-                __threadfence_system();
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(a.flag[j]), "l"(a.tag) : "memory");
-            }
-        }
-        __syncwarp();
-    }
-}
-
-// test knob RWR_DIST_PUSH_DELAY=<microseconds>: holds the copy engines back so that a gather that does not wait for its
-// slice reads stale data for sure (tests/test_gpu_partitioned.py, mode "overlapped_slow")
-__global__ void k_dist_delay(long long cycles) {
-    const long long t0 = clock64();
-    while (clock64() - t0 < cycles) __nanosleep(1000);
-}
-
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
     rwr_comm* c = g->comm;
     if (!c || c->n_ranks < 2 || c->fake) return;
@@ -309,74 +218,11 @@ void dist_setup_p2p(rwr_graph* g) {
     if (bad != 0.0) { dist_release_p2p(g); return; }
     g->p2p = true;
     if (g->ws_compact && dist_overlap_wanted(g)) {
-        int prio_lo = 0, prio_hi = 0;
-        CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        for (int k = 0; k < rwr_graph::XSTREAMS; k++)
-            CUDA_CHECK(cudaStreamCreateWithPriority(&g->xstream[k], cudaStreamNonBlocking, prio_hi));
         CUDA_CHECK(cudaMalloc((void**)&g->push_done, 8 * sizeof(unsigned)));
         CUDA_CHECK(cudaMemsetAsync(g->push_done, 0, 8 * sizeof(unsigned), st));
-        CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_fin, cudaEventDisableTiming));
-        for (int b = 0; b < 2; b++)
-            for (int k = 0; k < rwr_graph::XSTREAMS; k++) CUDA_CHECK(cudaEventCreateWithFlags(&g->ev_push[b][k], cudaEventDisableTiming));
+        CUDA_CHECK(cudaStreamSynchronize(st));
         g->overlap = true;
     }
-}
-
-void dist_before_iteration(rwr_graph* g, int b) {
-    if (!g->overlap || !g->push_pending[b]) return;
-    for (int k = 0; k < g->push_streams[b]; k++) CUDA_CHECK(cudaStreamWaitEvent(g->stream, g->ev_push[b][k], 0));
-    g->push_pending[b] = false;
-}
-
-void dist_push_slice(rwr_graph* g, int b, size_t elt, unsigned long long tag) {
-    if (!g->overlap) return;
-    rwr_comm* c = g->comm;
-    const int P = c->n_ranks, me = c->rank;
-    const size_t off = (size_t)g->row_begin * elt, len = (size_t)(g->row_end - g->row_begin) * elt;
-    DistSync* mine = (DistSync*)g->psync;
-    CUDA_CHECK(cudaEventRecord(g->ev_fin, g->stream));
-    static const bool use_ce = getenv("RWR_DIST_PUSH_CE") != nullptr;      // probe: copy engines instead of the push kernel
-    const int n_streams = use_ce ? rwr_graph::XSTREAMS : 1;
-    for (int k = 0; k < n_streams; k++) CUDA_CHECK(cudaStreamWaitEvent(g->xstream[k], g->ev_fin, 0));
-    static const long long delay_us = getenv("RWR_DIST_PUSH_DELAY") ? atoll(getenv("RWR_DIST_PUSH_DELAY")) : 0;
-    if (delay_us > 0)
-        for (int k = 0; k < n_streams; k++) k_dist_delay<<<1, 1, 0, g->xstream[k]>>>(delay_us * 1900);
-    if (use_ce) {
-        // peer me+1 first (it gathers from this slice first), the streams take the peers in turn
-        for (int j = 1; j < P; j++) {
-            const int peer = (me + j) % P;
-            cudaStream_t xs = g->xstream[(j - 1) % rwr_graph::XSTREAMS];
-            if (len)
-                CUDA_CHECK(cudaMemcpyAsync((unsigned char*)g->peer_px[b][peer] + off, (unsigned char*)g->px[b] + off, len, cudaMemcpyDefault, xs));
-            DistSync* theirs = (DistSync*)g->peer_psync[peer];
-            CUDA_CHECK(cudaMemcpyAsync(&theirs->arrive[me], &mine->tag_out[b], sizeof(unsigned long long), cudaMemcpyDefault, xs));
-        }
-    } else {
-        PushArgs a{};
-        a.src = (const unsigned char*)g->px[b] + off;
-        a.bytes16 = len & ~(size_t)15;
-        a.n_tail = (int)((len % 16) / 4);
-        a.n_peers = P - 1;
-        for (int j = 1; j < P; j++) {
-            const int peer = (me + j) % P;
-            a.dst[j - 1] = (unsigned char*)g->peer_px[b][peer] + off;
-            a.flag[j - 1] = &((DistSync*)g->peer_psync[peer])->arrive[me];
-        }
-        a.tag = tag;
-        a.done = g->push_done;
-        // the SM keeps ONE shared-memory / L1 split while CTAs of both kernels live on it: ask for the split k_spmv_ws runs with
-        CUDA_CHECK(cudaFuncSetAttribute(k_push_slices, cudaFuncAttributePreferredSharedMemoryCarveout, g->xchg_carveout_pct));
-        k_push_slices<<<g->sm_count, 32, 0, g->xstream[0]>>>(a);
-        KERNEL_CHECK();
-    }
-    for (int k = 0; k < n_streams; k++) CUDA_CHECK(cudaEventRecord(g->ev_push[b][k], g->xstream[k]));
-    g->push_streams[b] = n_streams;
-    g->push_pending[b] = true;
-}
-
-void dist_drain_pushes(rwr_graph* g) {
-    if (!g->overlap) return;
-    for (int b = 0; b < 2; b++) dist_before_iteration(g, b);
 }
 
 void dist_barrier(rwr_graph* g) {
@@ -393,13 +239,7 @@ void dist_barrier(rwr_graph* g) {
 // all ranks meet on the communicator, and only then does each rank free the buffers it exported -- cudaFree of memory a
 // peer still has open through cudaIpcOpenMemHandle is undefined behaviour.
 void dist_release_p2p(rwr_graph* g) {
-    for (int k = 0; k < rwr_graph::XSTREAMS; k++)
-        if (g->xstream[k]) { cudaStreamSynchronize(g->xstream[k]); cudaStreamDestroy(g->xstream[k]); g->xstream[k] = nullptr; }
     if (g->push_done) { cudaFree(g->push_done); g->push_done = nullptr; }
-    if (g->ev_fin) { cudaEventDestroy(g->ev_fin); g->ev_fin = nullptr; }
-    for (int b = 0; b < 2; b++)
-        for (int k = 0; k < rwr_graph::XSTREAMS; k++)
-            if (g->ev_push[b][k]) { cudaEventDestroy(g->ev_push[b][k]); g->ev_push[b][k] = nullptr; }
     g->overlap = false;
     if (!g->px[0] && !g->px[1] && !g->psync && g->peer_px[0].empty() && g->peer_px[1].empty()) { g->p2p = false; return; }
     const int me = dist_rank(g->comm);

@@ -16,23 +16,17 @@ void dist_release_p2p(rwr_graph* g);
 // every rank's slice of `vec` (elements of `elt` bytes, indexed by global row) to all ranks, in place
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt);
 
-// ---- overlapped exchange (default for up to 8 ranks with peer mapping; RWR_DIST_LEGACY=1 keeps the peer stores of the
-// epilogue kernel).  The edge stream of every rank is cut into slice-aligned blocks (stream.cu), k_finish_ws writes the
-// rank's slice of the next x locally only, the copy engines push it to the peers on a side stream -- peer r+1 first --
-// followed by an 8-byte arrival tag, and the next k_spmv_ws starts at once: it gathers from its own slice first and
-// waits, block by block, for the tags of the slices that are still in flight.
+// ---- overlapped exchange (default from 3 ranks on with peer mapping; RWR_DIST_LEGACY=1 keeps the peer stores of the
+// epilogue kernel, RWR_DIST_OVERLAP=1 forces it at 2 ranks).  The edge stream of every rank is cut into slice-aligned
+// blocks (stream.cu), k_finish_ws writes the rank's slice of the next x locally only, and the NEXT k_spmv_ws carries it
+// to the peers itself: a 17th warp per CTA drives TMA bulk copies into the peers' vectors (peer rank+1 first, then the
+// 8-byte arrival tag) while the other warps gather -- from the rank's own slice first, then block by block from the
+// slices whose tags have arrived.
 struct DistSync {
     unsigned long long arrive[8];     // arrive[s]: tag of the newest slice of rank s that is complete in this rank's vectors
-    unsigned long long tag_out[2];    // written by k_finish_ws: tag of the slice it just produced in vector b
 };
 bool dist_overlap_wanted(const rwr_graph* g);
-constexpr size_t DIST_PUSH_SMEM_BYTES = 14 * 1024;     // shared memory k_push_slices needs beside k_spmv_ws (3 x 4 KB + reserve)
-// before the iteration that will overwrite vector `b` (0 / 1): the earlier push out of that vector must be over
-void dist_before_iteration(rwr_graph* g, int b);
-// after k_finish_ws produced this rank's slice in vector `b`: push it to every peer, then the tag
-void dist_push_slice(rwr_graph* g, int b, size_t elt, unsigned long long tag);
-// the main stream waits for every push of this rank still in flight (before a collective that ends a run)
-void dist_drain_pushes(rwr_graph* g);
+constexpr size_t DIST_PUSH_SMEM_BYTES = 13 * 1024;     // shared memory the push warp needs behind the hub table (3 x 4 KB + barriers)
 void dist_barrier(rwr_graph* g);
 
 // ---- collectives of the partitioned build (graph.cu): in-place sums over the ranks and the all-to-all of the transpose

@@ -130,19 +130,13 @@ struct rwr_graph {
     bool p2p = false;
     void* px[2] = {nullptr, nullptr};     // (n + 8) * 8 bytes each, cudaMalloc
     std::vector<void*> peer_px[2];        // [n_ranks] the same buffers of every rank (own entry = px[b])
-    // overlapped exchange (dist.cu): every rank's slice of the next x travels to the peers by the copy engines on
-    // `xstream` while the next SpMV already runs; psync is the peer-mapped page of arrival tags
+    // overlapped exchange (dist.cu, stream.cu): the next k_spmv_ws pushes this rank's slice to the peers while it gathers;
+    // psync is the peer-mapped page of arrival tags
     bool overlap = false;
     void* psync = nullptr;                // DistSync, cudaMalloc, mapped by every peer
     std::vector<void*> peer_psync;        // [n_ranks]
-    static constexpr int XSTREAMS = 3;    // pushes to different peers ride different copy engines
-    cudaStream_t xstream[XSTREAMS] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ev_fin = nullptr, ev_push[2][XSTREAMS] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
-    bool push_pending[2] = {false, false};
-    int push_streams[2] = {0, 0};
-    unsigned* push_done = nullptr;        // [8] per-peer CTA counters of k_push_slices
-    int xchg_carveout_pct = 0;            // shared-memory carve-out (percent) k_spmv_ws and k_push_slices share on an SM
-    uint64_t xtag = 0;                    // tag of the last slice pushed (monotone over the life of the handle)
+    unsigned* push_done = nullptr;        // [8] per-peer CTA counters of the push warps
+    uint64_t xtag = 0;                    // tag of the last slice produced (monotone over the life of the handle)
 
     // fixed-count runs replay a captured CUDA graph of their n_iter x (k_spmv_ws, k_cutrows_ws, k_finish_ws) launches: small
     // graphs (the reference's ego networks are a few thousand nodes) are launch-bound otherwise.  One per precision.

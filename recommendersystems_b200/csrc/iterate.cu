@@ -129,14 +129,11 @@ static void launch_iteration(rwr_graph* g, const IterParams<T>& p, bool resid, d
     cudaStream_t st = g->stream;
     const bool parted = dist_n_ranks(g->comm) > 1;
     // on a row slice the convergence test needs the residual of all slices: it runs after the exchange
-    const int b_next = ((const void*)p.x_next == g->px[0]) ? 0 : 1;
-    if (g->overlap) dist_before_iteration(g, b_next);        // the copy engines are done with the vector this iteration overwrites
     ws_launch_iteration<T>(g, p, resid, thr, parted ? 0 : use_thr);
     static const bool skip_exchange = getenv("RWR_DIST_SKIP") != nullptr;      // timing probe only: wrong results
     if (parted && !skip_exchange) {
-        // x_next: pushed by the copy engines while the next SpMV runs (overlapped exchange), or already in every peer's copy
-        // when the epilogue stored it there (p.n_peers > 0), else NCCL
-        if (g->overlap) dist_push_slice(g, b_next, sizeof(T), p.tag_out_val);
+        // x_next: pushed by the next k_spmv_ws while it gathers (overlapped exchange), or already in every peer's copy when
+        // the epilogue stored it there (p.n_peers > 0), else NCCL
         dist_exchange(g, (p.n_peers || g->overlap) ? nullptr : p.x_next, sizeof(T), p.ctl->red);
         k_after_reduce<<<1, 1, 0, st>>>(p.ctl, thr, use_thr);
         KERNEL_CHECK();
@@ -187,12 +184,31 @@ static void set_exchange(rwr_graph* g, IterParams<T>& p, const void* x_next, boo
     p.compact = g->ws_compact ? 1 : 0;
     p.vrow_ptr = g->vrow_ptr.p; p.vpair = g->vpair.p;
     for (int k = 0; k < 8; k++) { p.blk_first_tile[k] = g->blk_first_tile[k]; p.blk_src[k] = ((me - k) % P + P) % P; }
-    p.arrive = nullptr; p.wait_tag = 0; p.tag_out = nullptr; p.tag_out_val = 0;
+    p.arrive = nullptr; p.wait_tag = 0;
+    p.push_src = nullptr; p.push_peers = 0; p.push_tail = 0; p.push_bytes16 = 0; p.push_done = g->push_done; p.push_delay = 0;
     if (g->overlap && live) {
-        DistSync* ds = (DistSync*)g->psync;
-        p.tag_out = &ds->tag_out[(x_next == g->px[0]) ? 0 : 1];
-        p.tag_out_val = ++g->xtag;
-        if (!first) { p.arrive = ds->arrive; p.wait_tag = p.tag_out_val - 1; }
+        // tag t marks the slices produced by the t-th iteration of this handle's life; all ranks count alike (collective calls)
+        const uint64_t tag = ++g->xtag;
+        if (!first) {
+            // this launch gathers from the vector the previous iteration produced (tag - 1): it pushes this rank's slice of it
+            // to the peers and waits for theirs
+            DistSync* ds = (DistSync*)g->psync;
+            p.arrive = ds->arrive;
+            p.wait_tag = tag - 1;
+            const int b = ((const void*)p.x == g->px[0]) ? 0 : 1;
+            const size_t off = (size_t)g->row_begin * sizeof(T), len = (size_t)(g->row_end - g->row_begin) * sizeof(T);
+            p.push_src = (const unsigned char*)g->px[b] + off;
+            p.push_bytes16 = len & ~(size_t)15;
+            p.push_tail = (int)((len % 16) / 4);
+            p.push_peers = P - 1;
+            for (int j = 1; j < P; j++) {
+                const int peer = (me + j) % P;
+                p.push_dst[j - 1] = (unsigned char*)g->peer_px[b][peer] + off;
+                p.push_flag[j - 1] = &((DistSync*)g->peer_psync[peer])->arrive[me];
+            }
+            static const long long delay_us = getenv("RWR_DIST_PUSH_DELAY") ? atoll(getenv("RWR_DIST_PUSH_DELAY")) : 0;
+            p.push_delay = delay_us * 1900;
+        }
     }
 }
 
@@ -312,9 +328,7 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
         if ((h.iters & 1) == 0 && n) CUDA_CHECK(cudaMemcpyAsync(y_out, ya, (size_t)n * sizeof(T), cudaMemcpyDeviceToDevice, st));
     }
     if (launched > 0) {
-        // every push of this rank is over before it enters the collective that ends the run: once the allGather returns,
-        // no peer is still writing into this rank's gather vectors either
-        dist_drain_pushes(g);
+        // (overlapped exchange: the pushes are part of the k_spmv_ws launches, nothing is in flight once they have run)
         dist_allgather_rows(g, y_out, sizeof(T));                     // row-partitioned: every rank gets the whole rank vector
     }
     CUDA_CHECK(cudaEventRecord(ev1, st));

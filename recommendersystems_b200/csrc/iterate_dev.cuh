@@ -54,8 +54,16 @@ struct IterParams {
     unsigned long long wait_tag;
     int blk_first_tile[8];  // tile holding the first link of stream block k (k = 0: this rank's own rows, never waited for)
     int blk_src[8];         // rank whose slice stream block k gathers from
-    unsigned long long tag_out_val;     // k_finish_ws: value stored to *tag_out by the last block (tag of the slice just produced)
-    unsigned long long* tag_out;
+    // the push warp of k_spmv_ws (overlapped exchange): while the other warps gather, it sends this rank's slice of the
+    // vector being gathered from (produced by the previous epilogue) to every peer, peer rank+1 first, then the tag wait_tag
+    const unsigned char* push_src;      // null: nothing to push (first iteration of a run)
+    unsigned char* push_dst[7];
+    unsigned long long* push_flag[7];   // arrive[rank] on those peers
+    int push_peers;
+    int push_tail;                      // 4-byte words after the 16-byte units
+    size_t push_bytes16;
+    unsigned* push_done;                // [7] CTAs that have finished a peer
+    long long push_delay;               // test knob: cycles the push warp sleeps first (late slices)
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers

@@ -425,7 +425,7 @@ void stream_prepare(rwr_graph* g) {
     if (parts > 1 && parts <= 8 && g->opts.hub_entries != 0 && (int)g->part_hot.size() == parts && !getenv("RWR_PART_NO_HUB")) {
         long cap = g->opts.hub_entries > 0 ? (long)g->opts.hub_entries : (long)((WS_HUB_AUTO_BYTES - WS_HDR) / 8);
         // overlapped exchange: k_push_slices lives beside k_spmv_ws on every SM; its buffers come out of the same 100 KB step
-        if (g->ws_compact) cap = std::min<long>(cap, (long)((WS_HUB_AUTO_BYTES - WS_HDR - DIST_PUSH_SMEM_BYTES - 1024) / 8));
+        if (g->ws_compact) cap = std::min<long>(cap, (long)((WS_HUB_AUTO_BYTES - WS_HDR - DIST_PUSH_SMEM_BYTES) / 8));
         if ((size_t)g->max_smem_optin > (size_t)WS_HDR) cap = std::min<long>(cap, (long)(((size_t)g->max_smem_optin - WS_HDR) / 8));
         long seg = cap / parts;
         for (int r = 0; r < parts; r++)                // a segment holds hot labels of ONE owner (ownership is deal_rows rounded to 32)
@@ -640,13 +640,88 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
 
 // Warps per CTA: 16 (128 registers each) everywhere but FP32 index-only, whose smaller register footprint lets 20 warps
 // fit without spills (+4.5 % there; 20 warps cost FP64 7 %: more sectors in flight than the L1 side holds).
-template <typename T, bool VALUED, bool XWAIT = false> struct WsCfg { static constexpr int WARPS = (sizeof(T) == 4 && !VALUED && !XWAIT) ? 20 : WS_WARPS; };
+template <typename T, bool VALUED, bool XWAIT = false> struct WsCfg {
+    // XWAIT: 15 gathering warps + the push warp = 16 (registers are allotted to a CTA in groups of four warps: a 17th warp
+    // would cost the other sixteen a fifth of their registers)
+    static constexpr int WARPS = XWAIT ? WS_WARPS - 1 : ((sizeof(T) == 4 && !VALUED) ? 20 : WS_WARPS);
+    static constexpr int THREADS = (WARPS + (XWAIT ? 1 : 0)) * 32;
+};
+
+// ---- the push warp of the overlapped exchange -----------------------------------------------------------------------
+// One warp of every k_spmv_ws CTA (XWAIT instantiation) sends this rank's slice of the gather vector to the peers while the
+// other sixteen gather: lane 0 drives the TMA -- bulk copies global -> shared (mbarrier) and shared -> peer memory (bulk
+// groups), three 4-KB buffers in flight per SM -- peer rank+1 first.  When the last CTA has finished a peer, it releases
+// the arrival tag there.  SM stores over NVLink reach ~750 GB/s where the copy engines managed ~350 GB/s for these
+// peer-mapped buffers, and a warp inside the kernel needs no second stream, no events and no shared-memory re-split.
+constexpr int PUSH_CHUNK = 4096;
+constexpr int PUSH_BUFS = 3;
+constexpr int PUSH_SMEM = PUSH_CHUNK * PUSH_BUFS + 128;          // buffers + mbarriers
+template <typename T>
+__device__ __noinline__ void ws_push_slices(const IterParams<T>& p, unsigned char* area /* 128-byte aligned */) {
+    const int lane = threadIdx.x & 31;
+    unsigned char* buf = area;
+    u64* bar = reinterpret_cast<u64*>(area + PUSH_CHUNK * PUSH_BUFS);
+    if (lane == 0) {
+        for (int s = 0; s < PUSH_BUFS; s++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[s])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (p.push_delay > 0) { const long long t0 = clock64(); while (clock64() - t0 < p.push_delay) __nanosleep(1000); }
+    }
+    __syncwarp();
+    const size_t n_chunks = (p.push_bytes16 + PUSH_CHUNK - 1) / PUSH_CHUNK;
+    u32 phase = 0;                                           // bit s: parity of buffer s's barrier
+    for (int j = 0; j < p.push_peers; j++) {
+        if (lane == 0) {
+            unsigned char* d = p.push_dst[j];
+            auto chunk_len = [&](size_t c) { return (u32)((c + 1) * PUSH_CHUNK <= p.push_bytes16 ? PUSH_CHUNK : p.push_bytes16 - c * PUSH_CHUNK); };
+            auto issue_load = [&](size_t c, int s) {
+                // the bulk store that read buffer s (PUSH_BUFS chunks ago) must be done reading it
+                asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PUSH_BUFS - 2) : "memory");
+                const u32 len = chunk_len(c);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[s])), "r"(len) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(buf + s * PUSH_CHUNK)),
+                             "l"(p.push_src + c * PUSH_CHUNK), "r"(len), "r"(smem_u32(&bar[s]))
+                             : "memory");
+            };
+            size_t c = blockIdx.x;
+            int s = 0;
+            if (c < n_chunks) issue_load(c, s);
+            while (c < n_chunks) {
+                const size_t cn = c + gridDim.x;
+                const int sn = (s + 1) % PUSH_BUFS;
+                if (cn < n_chunks) issue_load(cn, sn);
+                mbar_wait_a(smem_u32(&bar[s]), (phase >> s) & 1u);
+                phase ^= 1u << s;
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(d + c * PUSH_CHUNK), "r"(smem_u32(buf + s * PUSH_CHUNK)),
+                             "r"(chunk_len(c))
+                             : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                c = cn;
+                s = sn;
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // every store to this peer has completed
+            asm volatile("fence.proxy.async;" ::: "memory");
+        }
+        if (blockIdx.x == 0 && lane < p.push_tail)
+            reinterpret_cast<unsigned*>(p.push_dst[j] + p.push_bytes16)[lane] = reinterpret_cast<const unsigned*>(p.push_src + p.push_bytes16)[lane];
+        __threadfence_system();
+        __syncwarp();
+        if (lane == 0) {
+            const unsigned cdone = atomicAdd(&p.push_done[j], 1u);
+            if (cdone == gridDim.x - 1) {                  // every CTA's stores to this peer are out: hand over the tag
+                p.push_done[j] = 0;
+                __threadfence_system();
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.push_flag[j]), "l"(p.wait_tag) : "memory");
+            }
+        }
+        __syncwarp();
+    }
+}
 
 // DBG: the probe instantiation (rwr_profile_iteration with RWR_DEBUG_MODE) carries the ablation branches; the production
 // instantiation compiles none of them.
 // XWAIT: the instantiation for the overlapped exchange of a partitioned graph (waits for the peers' slices block by block).
 template <typename T, bool VALUED, bool DBG, bool XWAIT>
-__global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv_ws(const IterParams<T> p) {
+__global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::THREADS, 1) k_spmv_ws(const IterParams<T> p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (p.ctl->done) return;
     u32 smem0;
@@ -687,6 +762,15 @@ __global__ void __launch_bounds__(WsCfg<T, VALUED, XWAIT>::WARPS * 32, 1) k_spmv
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(hub_addr + off),
                          "l"(reinterpret_cast<const unsigned char*>(p.xhub) + off), "r"(len), "r"(smem0)
                          : "memory");
+        }
+    }
+    if constexpr (XWAIT) {
+        if ((int)(threadIdx.x >> 5) == WsCfg<T, VALUED, true>::WARPS) {            // the push warp
+            if (p.push_src) {
+                const size_t hub_bytes = ((size_t)p.hub * sizeof(T) + 127) & ~(size_t)127;
+                ws_push_slices<T>(p, smem_raw + WS_HDR + hub_bytes);
+            }
+            return;
         }
     }
     const u64 pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
@@ -943,7 +1027,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
             ctl->iters += 1;
             ctl->ticket = 0;
             ctl->tile_ctr = 0;                            // the next k_spmv_ws hands its tiles out from the start
-            if (p.tag_out) *p.tag_out = p.tag_out_val;    // the tag the copy engines hand to the peers after this slice
             if (p.parted) {                               // partial sums of this rank's rows: k_after_reduce finishes the job
                 ctl->red[0] = a;
                 ctl->red[1] = b;
@@ -972,7 +1055,7 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     auto kern = p.debug ? (valued ? k_spmv_ws<T, true, true, false> : k_spmv_ws<T, false, true, false>)
                         : p.arrive ? (valued ? k_spmv_ws<T, true, false, true> : k_spmv_ws<T, false, false, true>)
                                    : (valued ? k_spmv_ws<T, true, false, false> : k_spmv_ws<T, false, false, false>);
-    const int threads = (p.arrive ? WS_WARPS : (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS)) * 32;
+    const int threads = p.arrive ? WS_WARPS * 32 : (valued ? WsCfg<T, true>::WARPS : WsCfg<T, false>::WARPS) * 32;
     // the opt-in ceiling is a per-function, per-device setting shared by every handle and thread: always the device
     // maximum (a per-launch value would race between threads whose graphs have different hub sizes); the carve-out a
     // launch gets still follows the dynamic size it asks for
@@ -988,17 +1071,9 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
         pv.x = p.x - g->part_hub;
     }
     if (p.x_blocks > 1) pv.y = p.yv;              // the row sums of the virtual rows go to yv
-    if (g->ws_compact) {
-        // overlapped exchange: the push kernel shares the SM with this one; both ask for the same shared-memory / L1 split
-        // (the smallest step that holds both), or the second CTA would have to wait for an empty SM to change it
-        static const size_t steps_kb[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
-        const size_t need = smem + 1024 + DIST_PUSH_SMEM_BYTES;
-        size_t step = 228;
-        for (size_t s_kb : steps_kb) if (s_kb * 1024 >= need) { step = s_kb; break; }
-        g->xchg_carveout_pct = (int)(step * 100 / 228);
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, g->xchg_carveout_pct));
-    }
-    kern<<<ws_main_grid(g), threads, smem, g->stream>>>(pv);
+    // XWAIT: the buffers of the push warp sit behind the hub table
+    const size_t smem_launch = p.arrive ? (size_t)WS_HDR + (((size_t)p.hub * sizeof(T) + 127) & ~(size_t)127) + PUSH_SMEM : smem;
+    kern<<<ws_main_grid(g), threads, smem_launch, g->stream>>>(pv);
     KERNEL_CHECK();
 }
 template <typename T>
