@@ -12,6 +12,11 @@ A "step" is one pass of the hot path over one seed: init + 20 x (SpMV + cut rows
   roofline   dominant kernel k_spmv_ws against the measured HBM copy bandwidth (MEASURED_PEAKS.json); frac_iteration
              counts the two small kernels that finish an iteration (k_cutrows_ws, k_finish_ws) as well
   cpu_baseline  the CPU oracle (a port: the reference is C#, no toolchain here) on a bounded sample, rank 0, N=1 only
+  parity     BASELINE.md section 4 beside the throughput figures: transition matrix bit-exact on the full C2 graph, scores and
+             top-10 of the bench seed against the oracle (FP64 1e-12, FP32 1e-6 L1), the batched (C3) lists of 8 seeds
+Further legs of the same JSON line: `batched` (C3: 1,024 seeds through the SpMM tiles), `row_partitioned` (N > 1: one graph
+over all ranks, C4 itself at N = 8, with its own parity against an unpartitioned run), `c5` (Experiment-style evaluation:
+device-side hold-out, full-ranking hits / average precision, recall@10, oracle agreement on a sample).
 --impl reference times that CPU oracle alone, with min(10, nproc) threads over independent seeds (Program.cs:11).
 """
 from __future__ import annotations
@@ -430,9 +435,12 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
     # SURVEY 8(d), per GPU: E_p (4 + vb) + 4 (N_p + 1) + N vb + N_p vb
     alg = info.nnz / world * (4 + vb) + 4 * (info.n_nodes / world + 1) + info.n_nodes * vb + info.n_nodes / world * vb
     peak, _ = measured_peak_gbs()
-    return {"workload": f"C4-style: one synthetic Twitter-shaped graph ({info.n_nodes} nodes, {info.nnz} links) row-partitioned x{world}, "
-                        f"single seed, 20 iterations; the epilogue kernel stores each rank's slice of x into the peers' copies "
-                        f"over NVLink (CUDA IPC), 16-byte ncclAllReduce per iteration",
+    exchange = ("overlapped: the next SpMV pushes each rank's slice of x to the peers (TMA bulk copies over NVLink, CUDA IPC) while "
+                "it gathers, block by block as the slices arrive" if info.x_blocks == world and world > 1 else
+                "the epilogue kernel stores each rank's slice of x into the peers' copies over NVLink (CUDA IPC)")
+    return {"workload": f"C4-style: one synthetic Twitter-shaped graph ({info.n_nodes} nodes, {info.nnz} links) row-partitioned x{world} "
+                        f"(partitioned build: every rank generates and keeps the links of the sources it owns), single seed, "
+                        f"20 iterations; exchange {exchange}; 16-byte ncclAllReduce per iteration",
             "n_nodes": info.n_nodes, "nnz": info.nnz,
             "gteps": round(info.nnz * N_ITER * steps / (it_ms * 1e-3) / 1e9, 2), "ms_per_iteration": round(per_iter_ms, 4),
             "rows_rank0": [info.row_begin, info.row_end], "x_blocks": info.x_blocks,
@@ -441,7 +449,7 @@ def partitioned_leg(rs, dist, torch, spec, rank, world, local, seed, c, precisio
                     "peak": peak, "unit": "GB/s", "frac": round(alg / (per_iter_ms * 1e-3) / 1e9 / peak, 4)},
             "build": {"synth_ms": round(info.synth_ms, 1), "build_ms": round(info.build_ms, 1), "device_bytes": info.device_bytes},
             "nvlink": {"achieved_lower_bound": round(gathered / (per_iter_ms * 1e-3) / 1e9, 1), "peak": 900.0, "unit": "GB/s",
-                       "note": "bytes received per rank / whole iteration time (SpMV slice + epilogue with peer stores + allReduce)"},
+                       "note": "bytes received per rank / whole iteration time (SpMV slice + epilogue + allReduce); the exchange itself is hidden behind the SpMV"},
             "seed": seed, "top10_head": top[:3], "parity": parity}
 
 

@@ -88,14 +88,31 @@ __device__ __forceinline__ void accumulate(const MMParams<T>& p, const int* idx_
             ld_piece(p.x, src, piece, src < p.n_keep ? pol_keep : pol_stream, v[k]);
             if (VALUED) w[k] = val_s[qq];
         }
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const bool on = q + k * step < q1;
+        if (sizeof(T) == 4) {
+            // FP32 mode: the four products of a round are added in float (three additions of non-negative terms, <= 2 ulp of
+            // float) and enter the double accumulator as one value -- a quarter of the F2F.F64.F32 conversions and FP64
+            // additions, which share the narrow FP64 pipe (1e-6 L1 is the bar of this mode; the FP64 mode is untouched)
 #pragma unroll
             for (int c = 0; c < CW; c++) {
-                T t = v[k][c];
-                if (VALUED) t = mul_rn(t, w[k]);
-                acc[c] = __dadd_rn(acc[c], on ? (double)t : 0.0);
+                T part = (T)0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    T t = v[k][c];
+                    if (VALUED) t = mul_rn(t, w[k]);
+                    part = add_rn(part, (q + k * step < q1) ? t : (T)0);
+                }
+                acc[c] = __dadd_rn(acc[c], (double)part);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const bool on = q + k * step < q1;
+#pragma unroll
+                for (int c = 0; c < CW; c++) {
+                    T t = v[k][c];
+                    if (VALUED) t = mul_rn(t, w[k]);
+                    acc[c] = __dadd_rn(acc[c], on ? (double)t : 0.0);
+                }
             }
         }
     }
