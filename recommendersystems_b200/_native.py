@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librwr_b200.so")
+# RWR_B200_LIB: another build of the same library (the checked build: `make -C csrc CHECKED=1`)
+LIB_PATH = os.environ.get("RWR_B200_LIB") or os.path.join(_HERE, "librwr_b200.so")
 
 ABI_VERSION = 2
 RWR_OK = 0

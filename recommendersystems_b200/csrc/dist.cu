@@ -149,10 +149,10 @@ void synth_generate_device(rwr_graph* g, const rwr_synth_spec* spec);     // syn
 bool dist_overlap_wanted(const rwr_graph* g) {
     const rwr_comm* c = g->comm;
     if (!c || c->n_ranks < 2 || c->n_ranks > 8 || getenv("RWR_DIST_LEGACY") || getenv("RWR_DIST_NO_P2P")) return false;
-    // two ranks: the one 44-MB-class slice a rank sends rides inside the epilogue kernel almost for free (peer stores at
-    // NVLink rate while the kernel streams its rows), cheaper than the block bookkeeping of the overlapped form
-    // (profiles/r02_slice_probe.txt); from three ranks on the (P - 1)-fold egress would be exposed.  RWR_DIST_OVERLAP=1 forces it.
-    return c->n_ranks >= 3 || getenv("RWR_DIST_OVERLAP") != nullptr;
+    // Few ranks: the (P - 1) slices a rank sends ride inside the epilogue kernel at NVLink rate, cheaper than the block
+    // bookkeeping and the gathering warp the overlapped form gives up (measured, profiles/r02_part2.txt, r02_part8.txt:
+    // P = 2 0.414 ms against 0.45 ms overlapped, P = 4 0.585 against 0.599, P = 8 1.41 against 1.09).  RWR_DIST_OVERLAP=1 forces it.
+    return c->n_ranks >= 5 || getenv("RWR_DIST_OVERLAP") != nullptr;
 }
 
 void dist_setup_p2p(rwr_graph* g) {

@@ -16,7 +16,7 @@ void dist_release_p2p(rwr_graph* g);
 // every rank's slice of `vec` (elements of `elt` bytes, indexed by global row) to all ranks, in place
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt);
 
-// ---- overlapped exchange (default from 3 ranks on with peer mapping; RWR_DIST_LEGACY=1 keeps the peer stores of the
+// ---- overlapped exchange (default from 5 ranks on with peer mapping; RWR_DIST_LEGACY=1 keeps the peer stores of the
 // epilogue kernel, RWR_DIST_OVERLAP=1 forces it at 2 ranks).  The edge stream of every rank is cut into slice-aligned
 // blocks (stream.cu), k_finish_ws writes the rank's slice of the next x locally only, and the NEXT k_spmv_ws carries it
 // to the peers itself: a 17th warp per CTA drives TMA bulk copies into the peers' vectors (peer rank+1 first, then the

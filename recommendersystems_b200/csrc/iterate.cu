@@ -341,7 +341,9 @@ static void run_one(rwr_graph* g, RunWorkspace& ws, int seed_orig, double c, int
 
 // a k_spmv_ws that gave up waiting for a peer's slice leaves a mark: the results of that run are void
 static void check_exchange_fault(rwr_graph* g, const IterCtl* ctl) {
+#ifndef RWR_CHECKED
     if (!g->overlap) return;
+#endif
     IterCtl h{};
     CUDA_CHECK(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, g->stream));
     CUDA_CHECK(cudaStreamSynchronize(g->stream));
@@ -349,6 +351,7 @@ static void check_exchange_fault(rwr_graph* g, const IterCtl* ctl) {
         fprintf(stderr, "[rwr xchg r%d] %d iterations, warps waited %.3f ms in total for slices (%.4f ms per warp and iteration)\n",
                 dist_rank(g->comm), h.iters, (double)h.wait_clk / 1.9e6,
                 h.iters ? (double)h.wait_clk / 1.9e6 / (148.0 * 16.0) / h.iters : 0.0);
+    if (h.fault > 1) RWR_FAIL(RWR_E_INVALID, "checked build: index out of bounds in the iteration kernels (code %d)", h.fault);
     if (h.fault) RWR_FAIL(RWR_E_NCCL, "row-partitioned exchange: a peer's slice of x did not arrive in time (rank out of step or down)");
 }
 
@@ -474,7 +477,12 @@ void iterate_single_into(rwr_graph* g, int seed_orig, double c, int n_iter, T* y
     const int64_t l0 = g->pool.launches;
     int it = 0;
     double rs = 0;
-    if (ext0 && ext1 && !g->overlap) {
+#ifdef RWR_CHECKED
+    const bool must_check = true;
+#else
+    const bool must_check = g->overlap;
+#endif
+    if (ext0 && ext1 && !must_check) {
         // no host synchronisation: the workspace goes back to the scratch pool while the kernels are still queued, which is
         // safe because every later user of those blocks enqueues on the same stream
         run_one<T>(g, ws, seed_orig, c, 0, n_iter, 0.0, 0, y_out, &it, &rs, nullptr, ext0, ext1);

@@ -64,7 +64,19 @@ struct IterParams {
     size_t push_bytes16;
     unsigned* push_done;                // [7] CTAs that have finished a peer
     long long push_delay;               // test knob: cycles the push warp sleeps first (late slices)
+    // checked build (-DRWR_CHECKED, librwr_b200_checked.so): bounds of the gather index and of the row-sum store
+    int chk_src_end;        // stream sources are < this (n + hub + 8)
+    int chk_y_begin, chk_y_end;   // k_spmv_ws / k_cutrows_ws store row sums at [begin, end)
+    int chk_pairs;          // compact blocks: vpair entries are < this
 };
+
+// Checked build: an index outside its array leaves a code in IterCtl.fault (2 gather source, 3 row-sum store, 4 virtual row
+// of the epilogue) and the access is skipped; the run then fails with RWR_E_INVALID instead of corrupting memory.
+#ifdef RWR_CHECKED
+#define RWR_CHK(cond, ctl, code) ((cond) ? true : ((ctl)->fault = (code), false))
+#else
+#define RWR_CHK(cond, ctl, code) true
+#endif
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }

@@ -28,6 +28,7 @@ struct MMCtl {
     double seed_sum[MM_MAXB];
     int seed_flag[MM_MAXB];
     unsigned ticket;
+    int fault;             // checked build (-DRWR_CHECKED): a gather source outside [0, n)
 };
 
 template <typename T>
@@ -84,7 +85,10 @@ __device__ __forceinline__ void accumulate(const MMParams<T>& p, const int* idx_
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const u32 qq = (q + k * step < q1) ? q + k * step : q;        // clamped: always a valid slot
-            const int src = idx_s[qq];
+            int src = idx_s[qq];
+#ifdef RWR_CHECKED
+            if (src < 0 || src >= p.n) { p.ctl->fault = 2; src = 0; }
+#endif
             ld_piece(p.x, src, piece, src < p.n_keep ? pol_keep : pol_stream, v[k]);
             if (VALUED) w[k] = val_s[qq];
         }
@@ -396,6 +400,7 @@ __global__ void k_spmm_init(int n, MMParams<T> p, T* __restrict__ r0 /* may be n
     if (i == 0) {
         for (int c = 0; c < MM_MAXB; c++) { p.ctl->seed_sum[c] = 0.0; p.ctl->seed_flag[c] = 0; p.ctl->S[c] = 0.0; }
         p.ctl->ticket = 0;
+        p.ctl->fault = 0;
     }
     if (i >= (size_t)n * B) return;
     const int row = (int)(i / B), col = (int)(i % B);
@@ -497,6 +502,11 @@ void spmm_run_tile(rwr_graph* g, const int* seeds_int, int n_active, double c, i
         std::swap(x_cur, x_nxt);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));      // the workspace goes back to the handle's scratch pool on return
+#ifdef RWR_CHECKED
+    MMCtl h{};
+    CUDA_CHECK(cudaMemcpy(&h, ws.ctl.p, sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.fault) RWR_FAIL(RWR_E_INVALID, "checked build: k_spmm index out of bounds (code %d)", h.fault);
+#endif
 }
 
 template void spmm_run_tile<double>(rwr_graph*, const int*, int, double, int, double*, int64_t*);

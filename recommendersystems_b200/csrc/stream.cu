@@ -553,7 +553,10 @@ __device__ __forceinline__ void ws_gather_stage(const IterParams<T>& p, const in
     for (int j = 0; j < WS_R; j++)
 #pragma unroll
         for (int k = 0; k < 4; k++)
+        {
+            if (!RWR_CHK(s[j][k] >= 0 && s[j][k] < p.chk_src_end, p.ctl, 2)) { v[j][k] = (T)0; continue; }
             ws_ld_generic(v[j][k], (s[j][k] < p.hub ? hub_gen : xg) + (u64)(u32)s[j][k] * sizeof(T));
+        }
 #else
 #pragma unroll
     for (int j = 0; j < WS_R; j++)
@@ -630,7 +633,7 @@ __device__ __forceinline__ void ws_consume(const IterParams<T>& p, WsState& s, c
         acc = __dadd_rn(acc, v[k]);
         if (e & (1u << k)) {
             if (s.cont && row == s.first_row) p.head_partial[s.tile] = acc;
-            else if (!DBG || p.debug != 2) st_policy(p.y + row, (T)acc, pol_first);
+            else if ((!DBG || p.debug != 2) && RWR_CHK(row >= p.chk_y_begin && row < p.chk_y_end, p.ctl, 3)) st_policy(p.y + row, (T)acc, pol_first);
             row++;
             acc = 0.0;
         }
@@ -951,7 +954,7 @@ __global__ void __launch_bounds__(FIX_THREADS) k_cutrows_ws(const IterParams<T> 
         double total = 0.0;
         for (int i = m; i < t; i++) total = __dadd_rn(total, p.carry[i]);
         total = __dadd_rn(total, p.head_partial[t]);
-        p.y[row] = (T)total;
+        if (RWR_CHK(row >= p.chk_y_begin && row < p.chk_y_end, p.ctl, 3)) p.y[row] = (T)total;
     }
 }
 
@@ -982,7 +985,8 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
             const int i = row - p.row_begin;
             const u32 pb = p.vrow_ptr[i], pe = p.vrow_ptr[i + 1];
             y = (T)0;
-            for (u32 q = pb; q < pe; q++) y = add_rn(y, ld_stream(p.yv + p.vpair[q], pol_first));
+            for (u32 q = pb; q < pe; q++)
+                if (RWR_CHK(q < (u32)p.chk_pairs && p.vpair[q] < (u32)p.chk_pairs, ctl, 4)) y = add_rn(y, ld_stream(p.yv + p.vpair[q], pol_first));
         } else {
             y = ld_stream(p.y + row, pol_first);
         }
@@ -1061,6 +1065,9 @@ void ws_launch_spmv_only(rwr_graph* g, const IterParams<T>& p) {
     // launch gets still follows the dynamic size it asks for
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g->max_smem_optin));
     IterParams<T> pv = p;
+    pv.chk_src_end = g->n + p.hub + 8;
+    pv.chk_y_begin = p.x_blocks > 1 ? 0 : g->row_begin;
+    pv.chk_y_end = g->ws_compact ? g->v_compact : (p.x_blocks > 1 ? p.x_blocks * g->v_rows : g->row_end);
     pv.xhub = p.x;
     pv.hub_segs = 0;
     pv.hub_seg_len = 1;
@@ -1081,10 +1088,15 @@ void ws_launch_finish_only(rwr_graph* g, const IterParams<T>& p, bool resid, dou
     if (p.x_blocks > 1) {
         IterParams<T> pv = p;
         pv.y = p.yv;
+        pv.chk_y_begin = 0;
+        pv.chk_y_end = g->ws_compact ? g->v_compact : p.x_blocks * g->v_rows;
+        pv.chk_pairs = g->v_compact;
+        IterParams<T> pf = p;
+        pf.chk_pairs = g->v_compact;
         k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(pv);
         if (p.compact) {
-            if (resid) k_finish_ws<T, true, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
-            else k_finish_ws<T, false, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
+            if (resid) k_finish_ws<T, true, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(pf, thr, use_thr);
+            else k_finish_ws<T, false, 2><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(pf, thr, use_thr);
         } else {
             if (resid) k_finish_ws<T, true, 1><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
             else k_finish_ws<T, false, 1><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
@@ -1092,7 +1104,10 @@ void ws_launch_finish_only(rwr_graph* g, const IterParams<T>& p, bool resid, dou
         KERNEL_CHECK();
         return;
     }
-    k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(p);
+    IterParams<T> pc = p;
+    pc.chk_y_begin = g->row_begin;
+    pc.chk_y_end = g->row_end;
+    k_cutrows_ws<T><<<ws_fix_grid(g), FIX_THREADS, 0, g->stream>>>(pc);
     if (resid) k_finish_ws<T, true, 0><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
     else k_finish_ws<T, false, 0><<<ws_fin_grid(g), FIN_THREADS, 0, g->stream>>>(p, thr, use_thr);
     KERNEL_CHECK();
