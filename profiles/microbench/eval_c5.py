@@ -1,29 +1,25 @@
-"""C5 (BASELINE configs[4]) in one script: Experiment-style evaluation on a 10 M-node synthetic graph -- hold out the
-newest 10 % of the test users' likes, top-10 for every test user through the batched path, recall@10 and seeds/s.
+"""C5 (BASELINE configs[4]) in one script: Experiment-style evaluation on a 10 M-node synthetic graph -- device-side hold-out
+of the newest tenth of the test users' likes, full-ranking hits / average precision and recall@10 for every test user.
 usage: python profiles/microbench/eval_c5.py [n_test_users=2048] [scale=1.0]   (the full configuration is 100000 users)"""
-import sys, time; sys.path.insert(0, "."); sys.path.insert(0, "oracle")
-import numpy as np, recommendersystems_b200 as rs
-from recommendersystems_b200.experiment import hold_out_likes, recall_at_k
+import sys, time; sys.path.insert(0, ".")
+import numpy as np, recommendersystems_b200 as rs, bench
+from recommendersystems_b200.experiment import summarize
 n_users = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
 scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.0
-spec = dict(seed=20260105, n_users=int(1_000_000 * scale), n_items=int(9_000_000 * scale), n_third=0, authorship_per_mille=1000,
-            n_like=int(70_000_000 * scale), n_friend=int(20_000_000 * scale), n_follow=0, n_mention=0, undefined_per_mille=0,
-            scramble=1, p1_byte=61)
+spec = dict(bench.C5_SPEC)
+for k in ("n_users", "n_items", "n_like", "n_friend"):
+    spec[k] = int(spec[k] * scale)
 t0 = time.perf_counter()
-g0 = rs.Graph.synthetic(spec); links = g0.export_links(); g0.close()
-like_deg = np.bincount(links["src"][links["etype"] == 1], minlength=len(links["node_id"]))
-cand = np.flatnonzero(like_deg[:spec["n_users"]] >= 20)
-users = cand[(np.arange(n_users) * 7919) % len(cand)]
-users = np.unique(users)
-held, test = hold_out_likes(links, users, 0.1)
-g = rs.Graph.from_arrays(held["node_id"], held["node_type"], held["src"], held["dst"], held["etype"], held["w"]); g.buildGraph()
-print(f"graph {g.info().n_nodes} nodes {g.info().nnz} links, {len(users)} test users, {sum(len(t) for t in test.values())} held-out likes; "
+g = rs.Graph.synthetic(spec)
+cand = np.flatnonzero(g.degrees(raw=True)[:spec["n_users"]] >= 20)
+users = cand[np.unique(np.linspace(0, len(cand) - 1, min(n_users, len(cand))).astype(np.int64))].astype(np.int32)
+test = g.hold_out(users, 10, 9)
+g.buildGraph()
+print(f"graph {g.info().n_nodes} nodes {g.info().nnz} links, {len(users)} test users, {int(g.test_ptr[-1])} held-out likes; "
       f"setup {time.perf_counter() - t0:.1f} s", flush=True)
 for prec, pn in ((rs.FP64, "fp64"), (rs.FP32, "fp32")):
-    rec = rs.Recommender(g, prec)
-    rec.RecommendationBatch(users[:16], 0.15, 20, 10)
+    rs.evaluate_users(g, users[:16], None, 0.15, 20, k=10, precision=prec)
     t0 = time.perf_counter()
-    ids, sc, cnt = rec.RecommendationBatch(users, 0.15, 20, 10)
+    r = rs.evaluate_users(g, users, None, 0.15, 20, k=10, precision=prec)
     dt = time.perf_counter() - t0
-    r, hits, counted = recall_at_k(ids, cnt, users, test)
-    print(f"{pn}: {len(users)} users in {dt:.2f} s -> {len(users) / dt:.1f} seeds/s; recall@10 {r:.4f}, hits {hits}, users counted {counted}", flush=True)
+    print(pn, f"{len(users) / dt:.1f} users/s", summarize(r), flush=True)
