@@ -8,7 +8,8 @@ for anything that computes.
 from .rwr import (Comm, EdgeType, Feature, ForwardLink, Graph, Methodology, Model, Node, NodeType, Recommender, RwrError,
                   SynthSpec, FP32, FP64, evaluate, evaluate_users, methodology_masks, methodology_options, widen_float)
 from . import _native
+from .ingest import EgoNetwork, load_ego_network, run_experiment
 
 __all__ = ["Comm", "EdgeType", "Feature", "ForwardLink", "Graph", "Methodology", "Model", "Node", "NodeType", "Recommender",
            "RwrError", "SynthSpec", "FP32", "FP64", "evaluate", "evaluate_users", "methodology_masks", "methodology_options",
-           "widen_float", "_native"]
+           "widen_float", "_native", "EgoNetwork", "load_ego_network", "run_experiment"]

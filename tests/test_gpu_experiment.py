@@ -186,3 +186,52 @@ def test_k_fold_driver_matches_the_reference_loop(methodology):
     assert abs(out["map"] - sum_ap / 5) <= 1e-12
     tok = out["row"].split("\t")
     assert len(tok) == 7 and tok[:4] == [str(int(full["node_id"][ego])), str(methodology), "5", "10"] and tok[5] == str(int(deg[ego]))
+
+
+# ------------------------------------------------------------------------------------------ N4 -> N3 -> N2 -> hot path -> N1
+def _random_ego_db(path, seed=7, n_members=40, n_third=60, n_tweets=1500):
+    """A random ego network in the schema of SQLiteAdapter.cs:30-120 (ego 1000, mutual followees = members)."""
+    import sqlite3
+    rng = np.random.default_rng(seed)
+    c = sqlite3.connect(path)
+    c.executescript("CREATE TABLE follow(source INTEGER, target INTEGER); CREATE TABLE tweet(id INTEGER, author INTEGER);"
+                    "CREATE TABLE retweet(user INTEGER, tweet INTEGER); CREATE TABLE quote(user INTEGER, tweet INTEGER);"
+                    "CREATE TABLE favorite(user INTEGER, tweet INTEGER); CREATE TABLE mention(source INTEGER, target INTEGER);")
+    ego = 1000
+    members = [ego] + [1001 + i for i in range(n_members)]
+    third = [5000 + i for i in range(n_third)]
+    follow = []
+    for m in members[1:]:
+        follow += [(ego, m), (m, ego)]
+    for m in members:
+        for o in rng.choice(members, 8, replace=False):
+            if o != m:
+                follow.append((m, int(o)))
+        for t in rng.choice(third, 5, replace=False):
+            follow.append((m, int(t)))
+    c.executemany("INSERT INTO follow VALUES (?, ?)", follow)
+    tweets = [900000 + i for i in range(n_tweets)]
+    c.executemany("INSERT INTO tweet VALUES (?, ?)", [(t, int(rng.choice(members + third))) for t in tweets])
+    for table, k in (("retweet", 25), ("quote", 5), ("favorite", 40)):
+        rows = [(m, int(t)) for m in members for t in rng.choice(tweets, k, replace=False)]
+        c.executemany(f"INSERT INTO {table} VALUES (?, ?)", rows)
+    c.executemany("INSERT INTO mention VALUES (?, ?)", [(int(a), int(b)) for a, b in rng.choice(members, (600, 2)) if a != b])
+    c.commit()
+    c.close()
+
+
+@pytest.mark.parametrize("methodology", [8, 15, 9])
+def test_sqlite_ego_network_through_the_fold_loop(tmp_path, methodology):
+    """SQLite file -> ingest (N4) -> methodology masks (N3) -> device hold-out (N2) -> RWR -> device evaluation (N1), against
+    the same links through the CPU restatement of the fold loop; the MENTION weights make this the valued layout."""
+    from recommendersystems_b200.ingest import load_ego_network
+    db = str(tmp_path / "1000.sqlite")
+    _random_ego_db(db)
+    links, net = load_ego_network(db)
+    assert net.like_count() >= 60 and (links["etype"] == R.MENTION).sum() > 10 and (links["node_type"] == 3).sum() > 10
+    out = X.run_k_fold(links, methodology, n_folds=4, n_iter=12, ego=0, validate=False)
+    hits, sum_ap, folds = R.run_k_fold(links, methodology, 4, 12, 0)
+    assert out["hits"] == int(hits) == net.like_count()                  # every held-out like is found somewhere in the full ranking
+    assert [f["hits"] for f in out["folds"]] == [f[1] for f in folds]
+    assert abs(out["map"] - sum_ap / 4) <= 1e-12
+    assert out["row"].split("\t")[:4] == ["1000", str(methodology), "4", "12"]
