@@ -235,3 +235,23 @@ def test_sqlite_ego_network_through_the_fold_loop(tmp_path, methodology):
     assert [f["hits"] for f in out["folds"]] == [f[1] for f in folds]
     assert abs(out["map"] - sum_ap / 4) <= 1e-12
     assert out["row"].split("\t")[:4] == ["1000", str(methodology), "4", "12"]
+
+
+def test_evaluate_users_with_thousands_of_test_items():
+    """More test items in one seed tile than the shared-memory histogram of k_ev_hist holds (2 048): the global-memory form."""
+    full = O.synth_generate(SPEC)
+    users = like_users(full, SPEC["n_users"], 20, 3).tolist()
+    items = full["node_id"][full["node_type"] == 2]
+    rng = np.random.default_rng(5)
+    tsets = {u: rng.choice(items, 1500, replace=False).tolist() for u in users}       # 4 500 items in the tile
+    g = from_links(full)
+    g.buildGraph()
+    r = rs.evaluate_users(g, users, tsets, 0.15, 10, k=10)
+    og = O.OracleGraph(full["node_id"], full["node_type"], full["src"], full["dst"], full["etype"], full["w"])
+    assert og.build() == 0
+    for i, u in enumerate(users):
+        ids, _ = og.recommend(int(u), 0.15, 10)
+        h, ap, atk = R.evaluate_ranking(ids, tsets[u], 10)
+        assert (int(r["hits"][i]), int(r["hits_at_k"][i])) == (h, atk) and abs(float(r["avg_precision"][i]) - ap) <= 1e-12
+        assert 0 < h <= 1500                                  # liked tweets among the 1 500 are no candidates
+    g.close()
