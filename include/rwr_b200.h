@@ -146,7 +146,9 @@ int rwr_graph_get_info(rwr_graph* g, rwr_graph_info* info);     /* `Graph.size()
 /* raw links back on the host, in the canonical (source, insertion) order (`Graph.nodes`, `Graph.edges`)    */
 int rwr_graph_export_links(rwr_graph* g, int64_t* node_id, int32_t* node_type, int32_t* src, int32_t* dst,
                            int32_t* etype, double* w);
-/* `Graph.graph` (Graph.cs:43): row_ptr[N+1], col[nnz], val[nnz]; null rows have equal row_ptr entries      */
+/* `Graph.graph` (Graph.cs:43): row_ptr[N+1], col[nnz], val[nnz]; null rows have equal row_ptr entries.
+ * Not available on a row-partitioned handle (RWR_E_UNSUPPORTED: every rank holds the rows of its own sources only;
+ * rwr_graph_export_links returns those links, rwr_graph_get_degrees sums over the ranks and is a collective call). */
 int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val);
 /* `graph[i][k].type` (Graph.cs:73-74 copies the whole ForwardLink): the EdgeType of every explicit link, CSR order     */
 int rwr_graph_get_csr_types(rwr_graph* g, int32_t* etype /*[nnz]*/);

@@ -8,6 +8,7 @@
 //                               every held-out like leave the raw link list (stable compaction, insertion order kept)
 // The evaluation itself (N1, Experiment.cs:121-128) lives next to the top-k kernels in select.cu.
 #include <algorithm>
+#include <vector>
 
 #include "graph.h"
 #include "primitives.cuh"
@@ -215,6 +216,11 @@ extern "C" int rwr_graph_hold_out(rwr_graph* g, const int32_t* users, int32_t n_
     if (n_folds < 1 || fold < 0 || fold >= n_folds) RWR_FAIL(RWR_E_INVALID, "fold %d of %d", fold, n_folds);
     for (int i = 0; i < n_users; i++)
         if (users[i] < 0 || users[i] >= g->n) RWR_FAIL(RWR_E_BADSEED, "user %d outside [0, %d)", users[i], g->n);
+    {
+        std::vector<int32_t> sorted(users, users + n_users);
+        std::sort(sorted.begin(), sorted.end());
+        if (std::adjacent_find(sorted.begin(), sorted.end()) != sorted.end()) RWR_FAIL(RWR_E_INVALID, "a test user is listed twice");
+    }
     CUDA_CHECK(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
     AllocStream alloc_on(st);

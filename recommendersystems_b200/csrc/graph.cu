@@ -1019,6 +1019,7 @@ int rwr_graph_get_csr(rwr_graph* g, int64_t* row_ptr, int32_t* col, double* val)
     RWR_API_BEGIN
     if (!g) RWR_FAIL(RWR_E_INVALID, "graph is NULL");
     if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    if (g->part_build) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned handle: every rank holds the rows of W of the sources it owns only");
     CUDA_CHECK(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
     const size_t n = (size_t)g->n, nnz = (size_t)g->nnz;
@@ -1039,6 +1040,7 @@ int rwr_graph_get_csr_types(rwr_graph* g, int32_t* etype) {
     RWR_API_BEGIN
     if (!g || !etype) RWR_FAIL(RWR_E_INVALID, "NULL argument");
     if (!g->built) RWR_FAIL(RWR_E_NOT_BUILT, "buildGraph() has not run");
+    if (g->part_build) RWR_FAIL(RWR_E_UNSUPPORTED, "row-partitioned handle: every rank holds the rows of W of the sources it owns only");
     CUDA_CHECK(cudaSetDevice(g->device));
     cudaStream_t st = g->stream;
     AllocStream alloc_on(st);

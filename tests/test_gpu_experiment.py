@@ -63,6 +63,8 @@ def test_hold_out_rejects_a_built_graph_and_bad_arguments():
         g.hold_out([0], 3, 3)
     with pytest.raises(KeyError):
         g.hold_out([len(full["node_id"])], 3, 0)
+    with pytest.raises(rs.RwrError):
+        g.hold_out([0, 5, 0], 3, 0)                    # a user listed twice
     g.buildGraph()
     with pytest.raises(ValueError):
         g.hold_out([0], 3, 0)
