@@ -14,18 +14,7 @@ constexpr int IDX_PAD = 8;                                        // ints of sla
 
 struct rwr_comm;
 
-// Partitioned build: which rank holds the raw links of a source node.  The node range is cut into up to three segments
-// (the synthetic generator: users, items, third-party users -- their degrees differ by an order of magnitude, and ids
-// inside a class are scrambled) and every segment is dealt evenly over the ranks in contiguous pieces.
-struct OwnMap {
-    int parts = 1, rank = 0, n_segs = 1;
-    long long seg[5] = {0, 0, 0, 0, 0};       // segment k = [seg[k], seg[k + 1]), none empty
-};
-__host__ __device__ inline int own_rank(const OwnMap& m, long long i) {
-    int k = 0;
-    while (k + 1 < m.n_segs && i >= m.seg[k + 1]) k++;
-    return (int)(((i - m.seg[k]) * m.parts) / (m.seg[k + 1] - m.seg[k]));
-}
+#include "ownmap.h"
 
 struct rwr_graph {
     int device = 0;
