@@ -464,6 +464,33 @@ int orc_model_run(void* h, int32_t seed, double damping, int32_t mode, int32_t n
     return rc;
 }
 
+// NOT the reference: the same seeded fixed-count iteration (collapsed form) with every accumulator in x87 extended
+// precision (64-bit significand) and only the final ranks rounded to double -- a yardstick for how much of a difference
+// between two double-precision evaluations is rounding noise of the summation order (oracle/rounding_study.py).
+int orc_model_run_extended(void* h, int32_t seed, double damping, int32_t n_iter, double* rank_out) {
+    OrcGraph* g = (OrcGraph*)h;
+    if (!g || !g->built || seed < 0 || seed >= g->n) return ORC_E_INVALID;
+    const int n = g->n;
+    std::vector<long double> rank(n, 0.0L), next(n, 0.0L);
+    rank[seed] = (long double)n;
+    const long double omc = 1.0L - (long double)damping;
+    for (int it = 0; it < n_iter; it++) {
+        for (int i = 0; i < n; i++) {
+            const int64_t b = g->row_ptr[i], e = g->row_ptr[i + 1];
+            if (e > b) {
+                const long double rw = omc * rank[i];
+                for (int64_t w = b; w < e; w++) next[g->col[w]] += rw * (long double)g->val[w];
+                next[seed] += rank[i] - rw;
+            } else {
+                next[seed] += rank[i];
+            }
+        }
+        for (int i = 0; i < n; i++) { rank[i] = next[i]; next[i] = 0.0L; }
+    }
+    for (int i = 0; i < n; i++) rank_out[i] = (double)rank[i];
+    return ORC_OK;
+}
+
 // Recommendation(idx, c, nIter[, topN]); `damping` is the already widened float (Recommender.cs:16).
 // top_n < 0: the 3-argument overload (full ranking).  The 4-argument overload returns the WHOLE list when
 // topN <= 0 (the `Count == topN` test at Recommender.cs:47 never fires) -- kept.
