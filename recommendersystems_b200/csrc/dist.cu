@@ -1,15 +1,20 @@
-// dist.cu -- K10: row-partitioned mode for one graph spread over several GPUs (no reference analogue).
+// dist.cu -- K10: row-partitioned mode for one graph spread over several GPUs (no reference analogue): the communicator,
+// the peer mapping, the collectives of the partitioned build.
 //
 // Every rank owns a contiguous block of rows of W^T (the destination nodes) with its own edge stream (stream.cu).  The
 // internal labels are dealt over the slices (k_deal_labels, graph.cu): hot nodes one by one, clustered cold nodes in
 // blocks, so the slices hold near-equal row counts and near-equal link counts and both the SpMV and the exchange are
-// balanced.  An iteration on a rank needs the whole gather vector x and produces the slice of the next one for its rows:
-//   * peer path (default, up to 8 ranks): the two gather vectors of every rank are mapped into every other rank through
-//     CUDA IPC, and k_finish_ws stores each new entry into all copies over NVLink / NVSwitch while it computes it;
+// balanced.  An iteration on a rank needs the whole gather vector x and produces the slice of the next one for its rows.
+// The two gather vectors of every rank (and a page of arrival tags) are mapped into every other rank through CUDA IPC:
+//   * overlapped exchange (default from 5 ranks on): k_finish_ws writes the slice locally, the NEXT k_spmv_ws pushes it to
+//     the peers with a TMA-driving warp per CTA while the other warps gather block by block as the slices arrive (stream.cu);
+//   * peer stores (up to 4 ranks, or RWR_DIST_LEGACY=1): k_finish_ws stores each new entry into all copies over NVLink;
 //   * NCCL path (fallback: RWR_DIST_NO_P2P=1, more than 8 ranks, or a mapping that fails on any rank): one grouped set
 //     of in-place ncclBroadcast calls per iteration (the slices have unequal lengths).
-// Either way the two scalars every rank needs -- the restart mass S and the L1 residual -- are summed with one 16-byte
-// ncclAllReduce, which is also the barrier that orders the peer stores of one iteration before the gathers of the next.
+// In every form the two scalars every rank needs -- the restart mass S and the L1 residual -- are summed with one 16-byte
+// ncclAllReduce, which is also the barrier of the iteration: a rank can only be one allReduce ahead of its peers, so the
+// vector it writes remotely is never the one a peer still gathers from.
+// The partitioned build (graph.cu) uses dist_allreduce_sum / dist_alltoallv below.
 // NCCL is bound at run time (dlopen) so that a single-GPU host needs no NCCL at all.
 #include <dlfcn.h>
 
@@ -92,7 +97,6 @@ bool dist_is_fake(const rwr_comm* c) { return c && c->fake; }
 int dist_rank(const rwr_comm* c) { return c ? c->rank : 0; }
 int dist_n_ranks(const rwr_comm* c) { return c ? c->n_ranks : 1; }
 
-__global__ void k_dist_noop() {}
 void dist_allgather_rows(rwr_graph* g, void* vec, size_t elt) {
     rwr_comm* c = g->comm;
     if (!c || c->n_ranks < 2 || c->fake) return;

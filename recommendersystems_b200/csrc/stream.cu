@@ -28,6 +28,14 @@
 // row ends runs a warp-level segmented scan with early exit, and the lanes holding a row end store the sums.  The open
 // row at a tile boundary goes to tail[t] / head[t].  No floating-point atomics anywhere: a run is bit-reproducible; the
 // association of a row sum differs from the reference's sequential one by O(log deg) ulp (all addends >= 0).
+//
+// Row-partitioned graphs (K10, dist.cu) reuse the same kernels on a rank's rows:
+//   * the hub table holds the hottest labels of EVERY slice (HubMap: the stream stores table slots / shifted labels);
+//   * the stream can be cut into column blocks: padded virtual rows (rwr_opts.x_blocks), or -- for the overlapped exchange --
+//     compact slice-aligned blocks, block k = the links whose source belongs to rank (r - k) mod P (k_pair_*,
+//     k_ws_fill_compact), added up per row by k_finish_ws<.., 2> through a CSR of (row, block) pairs;
+//   * the XWAIT instantiation of k_spmv_ws has 15 gathering warps that wait, block by block, for the arrival tags of the
+//     peers' slices, and one push warp (ws_push_slices) that sends this rank's slice to the peers with TMA bulk copies.
 #include <algorithm>
 #include <climits>
 #include <cmath>
