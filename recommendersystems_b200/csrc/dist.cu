@@ -210,33 +210,24 @@ void dist_setup_p2p(rwr_graph* g) {
             }
         }
     }
-    // all ranks must agree: one failing mapping anywhere sends everybody to the NCCL path
+    // all ranks must agree: one failing mapping anywhere sends everybody to the NCCL path, and the overlapped exchange needs
+    // the slice-aligned stream on EVERY rank (a rank without a single link in its rows builds a plain, empty stream)
     DevBuf<double> flag;
-    flag.alloc(1);
-    const double mine_bad = ok ? 0.0 : 1.0;
-    CUDA_CHECK(cudaMemcpyAsync(flag.p, &mine_bad, sizeof(double), cudaMemcpyHostToDevice, st));
-    NCCL_CHECK(api.AllReduce(flag.p, flag.p, 1, ncclFloat64, ncclSum, c->comm, st));
-    double bad = 0.0;
-    CUDA_CHECK(cudaMemcpyAsync(&bad, flag.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    flag.alloc(2);
+    const double mine_bad[2] = {ok ? 0.0 : 1.0, (g->ws_compact && dist_overlap_wanted(g)) ? 0.0 : 1.0};
+    CUDA_CHECK(cudaMemcpyAsync(flag.p, mine_bad, sizeof(mine_bad), cudaMemcpyHostToDevice, st));
+    NCCL_CHECK(api.AllReduce(flag.p, flag.p, 2, ncclFloat64, ncclSum, c->comm, st));
+    double bad[2] = {0.0, 0.0};
+    CUDA_CHECK(cudaMemcpyAsync(bad, flag.p, sizeof(bad), cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));
-    if (bad != 0.0) { dist_release_p2p(g); return; }
+    if (bad[0] != 0.0) { dist_release_p2p(g); return; }
     g->p2p = true;
-    if (g->ws_compact && dist_overlap_wanted(g)) {
+    if (bad[1] == 0.0) {
         CUDA_CHECK(cudaMalloc((void**)&g->push_done, 8 * sizeof(unsigned)));
         CUDA_CHECK(cudaMemsetAsync(g->push_done, 0, 8 * sizeof(unsigned), st));
         CUDA_CHECK(cudaStreamSynchronize(st));
         g->overlap = true;
     }
-}
-
-void dist_barrier(rwr_graph* g) {
-    rwr_comm* c = g->comm;
-    if (!c || c->n_ranks < 2 || c->fake) return;
-    DevBuf<double> d;
-    d.alloc(1);
-    CUDA_CHECK(cudaMemsetAsync(d.p, 0, sizeof(double), g->stream));
-    NCCL_CHECK(nccl().AllReduce(d.p, d.p, 1, ncclFloat64, ncclSum, c->comm, g->stream));
-    CUDA_CHECK(cudaStreamSynchronize(g->stream));
 }
 
 // Teardown in three steps (collective on a partitioned handle): every rank closes its mappings of the peers' buffers,
