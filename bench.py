@@ -644,10 +644,24 @@ def c1_literal_leg():
     seed = int(np.flatnonzero(np.bincount(links["src"], minlength=og.n)[:1000] > 0)[0])
     iters = 5
     t0 = time.perf_counter()
-    og.run(seed, O.widen_float(C_FLOAT), n_iter=iters, literal=True)
+    want, _ = og.run(seed, O.widen_float(C_FLOAT), n_iter=iters, literal=True)
     cpu_s = (time.perf_counter() - t0) * N_ITER / iters
     nnz_c1 = og.nnz()
     og.close()
+    # the reference ITSELF where its compiled sources travelled with the repo (oracle/_ref/libref.so, `make -C oracle ref`):
+    # Graph.cs / Model.cs / Recommender.cs as written, through oracle/cs2cpp.py -- and it must agree with the port bit for bit
+    import ref as RF
+    reference = None
+    if RF.available(build=False):
+        rg = RF.ReferenceGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+        assert rg.build() == 0
+        t0 = time.perf_counter()
+        got, _ = rg.run(seed, O.widen_float(C_FLOAT), n_iter=iters)
+        ref_s = (time.perf_counter() - t0) * N_ITER / iters
+        rg.close()
+        reference = {"kind": "reference", "how": "the reference's own Graph.cs / Model.cs compiled by g++ after oracle/cs2cpp.py respelt the "
+                     "declarations (no C# toolchain in this image)", "cpu_seconds_per_request": round(ref_s, 3),
+                     "bit_identical_to_port": bool(np.array_equal(got.view(np.uint64), want.view(np.uint64)))}
     g = rs.Graph.from_arrays(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
     g.buildGraph()
     rec = rs.Recommender(g)
@@ -660,7 +674,8 @@ def c1_literal_leg():
     g.close()
     return {"workload": f"C1: ego network of {len(links['node_id'])} nodes / {nnz_c1} links, Model.run(20), literal O(N^2) loops, 1 core",
             "cpu_seconds_per_request": round(cpu_s, 3), "sample": f"{iters} of 20 iterations, scaled",
-            "gpu_seconds_per_request": round(gpu_s, 6), "gpu_api": "Recommender.Recommendation(seed, 0.15f, 20, 10)"}
+            "gpu_seconds_per_request": round(gpu_s, 6), "gpu_api": "Recommender.Recommendation(seed, 0.15f, 20, 10)",
+            "reference_itself": reference}
 
 
 # ======================================================================================================= reference arm

@@ -157,6 +157,52 @@ def test_golden_recommendation(name, opts):
         assert [p[0] for p in k20] == [p[0] for p in full][:20]
 
 
+def test_fixture_written_by_the_reference():
+    """tests/golden/ref_mid.json holds what the reference's OWN Graph.cs / Model.cs / Recommender.cs compute on an 820-node ego
+    network (oracle/make_golden_ref.py, through oracle/cs2cpp.py): the CUDA path against the reference itself, no oracle between."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "ref_mid.json")) as f:
+        want = json.load(f)
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    for from_generator in (False, True):               # the CPU generator's links uploaded / the device generator's own
+        if from_generator:
+            gg = rs.Graph.synthetic(want["spec"])
+            gg.buildGraph()
+        else:
+            gg = gpu_graph(O.synth_generate(want["spec"]))
+        assert gg.size() == want["n_nodes"]
+        rp, col, val = gg.csr()
+        assert (len(col), int((np.diff(rp) == 0).sum())) == (want["csr"]["nnz"], want["csr"]["dangling_rows"])
+        assert sha(rp.astype(np.int64)) == want["csr"]["row_ptr_sha256"] and sha(col.astype(np.int32)) == want["csr"]["col_sha256"]
+        assert sha(val.astype(np.float64)) == want["csr"]["val_sha256"]                      # A1-A3 bit for bit
+        rec = rs.Recommender(gg)
+        for e in want["seeds"]:
+            for n, ranks in e["ranks"].items():
+                m = rs.Model(gg, C015, e["seed"])
+                m.run(int(n))
+                assert_close_fp64(m.rank, unhex(ranks), f"seed {e['seed']} iter {n}")
+            for thr, w in e["thresholds"].items():
+                m = rs.Model(gg, C015, e["seed"])
+                m.run(float(thr))
+                assert m.nIterations == w["iters"], (e["seed"], thr)
+            w = e["recommendation"]
+            full = rec.Recommendation(e["seed"], want["damping_float"], w["n_iter"])
+            assert len(full) == len(w["ids"])
+            top10 = unhex(w["top10_scores"])
+            assert_close_fp64([p[1] for p in full[:10]], top10)
+            same_ranking([p[0] for p in full[:10]], [p[1] for p in full[:10]], w["ids"][:10], top10)
+            top = rec.Recommendation(e["seed"], want["damping_float"], w["n_iter"], 10)
+            same_ranking([p[0] for p in top], [p[1] for p in top], w["ids"][:10], top10)
+            # beyond the stored scores: the same SET of candidates, and the long tail of exact zeros in id-descending order
+            assert sorted(p[0] for p in full) == sorted(w["ids"])
+            zeros = [p[0] for p in full if p[1] == 0.0]
+            assert zeros == w["ids"][len(w["ids"]) - len(zeros):] and zeros == sorted(zeros, reverse=True)
+        gg.close()
+
+
 def test_kat_8c_spelled_out():
     g = load_golden("kat_8c")
     gg = gpu_graph(g["input"])
