@@ -4,9 +4,10 @@
 
 Every number is produced by the pure-Python literal restatement (oracle/rwr_literal.py) of
 Graph.cs / Model.cs / Recommender.cs, i.e. by executing the reference's statements one by one in
-IEEE double.  The reference itself cannot be run here (C#, no toolchain, no tests/fixtures of its
-own: PARITY UNPINNED), so these files freeze the restatement; tests then require the C++ oracle and
-the CUDA path to reproduce them.  Floats are stored as C99 hex strings (bit-exact).
+IEEE double.  The reference has no tests or fixtures of its own and no C# runtime exists here; its sources
+compiled for g++ (oracle/cs2cpp.py -> oracle/_ref/libref.so) reproduce every file written here bit for bit
+(tests/test_reference_pin.py), and oracle/make_golden_ref.py writes one more fixture with the reference itself.
+Tests then require the C++ oracle and the CUDA path to reproduce them.  Floats are stored as C99 hex strings (bit-exact).
 
 The synthetic-generator fixture is produced by a third, pure-Python implementation of this repo's
 generator spec (include/rwr_b200.h), independent of the C++ and CUDA ones.

@@ -8,10 +8,10 @@ are bit-identical to a strict-double execution of the C# code.  It is used
   * to generate the fixtures under tests/golden/ (see oracle/make_golden.py),
   * as an independent cross-check of the C++ oracle (oracle/rwr_oracle.cpp).
 
-PARITY UNPINNED: the reference ships no tests, fixtures or golden vectors and no C#
-toolchain (mono/dotnet/csc) exists in this image, so this restatement cannot be pinned
-against an execution of the reference itself.  Two independent restatements (this file
-and the C++ one) are required to agree bit for bit instead.
+PINNING: the reference ships no tests, fixtures or golden vectors and no C# runtime exists in
+this image.  Since round 2 the golden files this module writes are checked against the reference's
+own sources compiled for g++ (oracle/cs2cpp.py -> oracle/_ref/libref.so, tests/test_reference_pin.py):
+every vector is reproduced bit for bit.  This file stays as the third, independent restatement.
 
 Only small graphs: the restart loops are the reference's literal O(N^2) form.
 """

@@ -10,10 +10,15 @@
 //   /root/reference/Recommenders/RWRBased/Recommender.cs:14-51  Recommendation (+ topN overload)
 //   /root/reference/TweetRecommender/Experiment.cs:121-128      hits / average precision
 //
-// PARITY UNPINNED: the reference holds no tests, fixtures or golden vectors for this path and no
-// C# toolchain exists in this image, so the restatement is pinned only against (a) the hand-derived
-// known-answer vector of SURVEY.md section 8c and (b) an independent pure-Python restatement
-// (oracle/rwr_literal.py) that must agree bit for bit (tests/test_oracle_*.py).
+// PINNING.  The reference holds no tests, fixtures or golden vectors for this path and no C# runtime exists in this
+// image, so it cannot be executed as a .NET assembly.  Its sources are compiled instead: `make -C oracle ref` respells the
+// declarations of Graph.cs / Model.cs / Recommender.cs for g++ (oracle/cs2cpp.py, syntactic rules only, every statement
+// and expression untouched) from where they lie under /root/reference -> oracle/_ref/libref.so.  tests/test_reference_pin.py
+// holds this restatement to that library bit for bit (golden vectors, random graphs with dangling / multi-edge / NaN / Inf
+// rows, exceptions, the C1 graph), next to (a) the hand-derived known-answer vector of SURVEY.md section 8c and (b) an
+// independent pure-Python restatement (oracle/rwr_literal.py).  What the compiled sources cannot show is the .NET runtime
+// itself: double arithmetic is IEEE binary64 on both sides (RyuJIT x64 / SSE2), List.Sort's algorithm differs but sorts a
+// total order on distinct ids, Dictionary / List / array semantics are oracle/ref_shim.hpp's.
 //
 // Two iteration forms:
 //   literal   -- the O(N^2) restart loops exactly as written (Model.cs:92-93, :96-97);
