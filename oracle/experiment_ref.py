@@ -37,8 +37,8 @@ def split_like_history(like_ids, n_folds: int, fold: int):
 
 def hold_out(links: dict, users, n_folds: int, fold: int):
     """The graph DataLoader builds when the fold's likes of every user in `users` are test data: the links u -> t and
-    t -> u of type LIKE are never added (DataLoader.cs:287-298 runs only over the training set).
-    -> (links without them, {user: testSet ids ascending})."""
+    t -> u of type LIKE are never added (DataLoader.cs:287-298 runs only over the training set), and a tweet nobody likes
+    any more is no node at all.  -> (links without them, {user: testSet ids ascending})."""
     src, dst, et = links["src"], links["dst"], links["etype"]
     node_id, node_type = links["node_id"], links["node_type"]
     n = len(node_id)
@@ -61,8 +61,25 @@ def hold_out(links: dict, users, n_folds: int, fold: int):
         hk = np.unique(np.concatenate(held_pairs))
         key = src.astype(np.int64) * n + dst
         drop |= (et == LIKE) & np.isin(key, hk)
+    # A held-out tweet that no user likes any more does not exist in the reference's graph at all: DataLoader creates a tweet
+    # node only while it walks somebody's likes (:291-303), and addAuthorship skips tweets that are not nodes (:355-356).  Here
+    # the node index stays (indices must not shift), but every link that still touches it goes and its type becomes UNDEFINED,
+    # so that it is no candidate of Recommender.cs:29 and can never be a hit of Experiment.cs:124.
+    node_type = node_type.copy()
+    if held_pairs:
+        held_tweets = np.unique(np.concatenate(held_pairs) // n)
+        still = (et == LIKE) & ~drop & (node_type[dst] == ITEM)
+        liked = np.zeros(n, bool)
+        liked[dst[still]] = True
+        orphans = held_tweets[~liked[held_tweets]]
+        if len(orphans):
+            gone = np.zeros(n, bool)
+            gone[orphans] = True
+            drop |= gone[src] | gone[dst]
+            node_type[orphans] = 0
     keep = ~drop
     out = dict(links)
+    out["node_type"] = node_type
     for k in ("src", "dst", "etype", "w"):
         out[k] = links[k][keep]
     return out, test
@@ -72,7 +89,8 @@ def apply_methodology(links: dict, methodology: int) -> dict:
     """What Experiment hands to `new Graph(nodes, edges)` for `methodology`, starting from the network with every relation
     loaded: relations of features that are not in the list are not there at all (DataLoader.cs:235-250), FRIENDSHIP links
     of methodologies 4 / 9 / 14 are retyped UNDEFINED (Experiment.cs:84-101), and MENTION weights are
-    nFriendhips * ln(cnt) / sum (DataLoader.cs:431) -- exactly 0.0 when no FRIENDSHIP link was loaded."""
+    nFriendhips * ln(cnt) / sum (DataLoader.cs:431) -- exactly 0.0 when no FRIENDSHIP link was loaded, and absent for a member
+    that owns no other link then (DataLoader.cs:403-405)."""
     feats = FEATURES[int(methodology)]
     et = links["etype"].copy()
     w = links["w"].copy()
@@ -86,6 +104,12 @@ def apply_methodology(links: dict, methodology: int) -> dict:
     if M not in feats:
         keep &= et != MENTION
     elif F not in feats:
+        # addMentionCount2 walks the members that already own an `allLinks` entry (DataLoader.cs:403-405): a member none of
+        # whose other relations was loaded gets no mention links at all (a dangling row, not a row of zero weights); the
+        # others get them with nFriendhips = 0, i.e. weight exactly 0.0
+        carrier = np.zeros(len(links["node_id"]), bool)
+        carrier[links["src"][keep & (et != MENTION) & (et != 0)]] = True
+        keep &= ~((et == MENTION) & ~carrier[links["src"]])
         w[et == MENTION] = 0.0
     if int(methodology) in RETYPE_FRIENDSHIP:
         et[et == FRIENDSHIP] = 0

@@ -16,7 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref.so")
-HEADER_PATH = os.path.join(_HERE, "_ref", "reference_rwr.hpp")
+HEADER_PATHS = (os.path.join(_HERE, "_ref", "reference_rwr.hpp"), os.path.join(_HERE, "_ref", "reference_experiment.hpp"))
 REFERENCE_ROOT = "/root/reference"
 _LIB = None
 
@@ -47,6 +47,16 @@ def lib() -> C.CDLL:
         L.ref_model_run.argtypes = [vp, i32, f64, i32, i32, f64, i64, vp, vp]
         L.ref_recommend.restype = i64
         L.ref_recommend.argtypes = [vp, i32, C.c_float, i32, i32, i32, vp, vp, i64]
+        cp = C.c_char_p
+        L.ref_db_reset.argtypes = [cp]
+        L.ref_db_add.argtypes = [cp, cp, vp, vp, i64]
+        L.ref_loader_validation.argtypes = [cp, i32, vp, vp, vp]
+        L.ref_loader_run.restype = vp
+        L.ref_loader_run.argtypes = [cp, i32, i32, i32]
+        L.ref_loader_destroy.argtypes = [vp]
+        L.ref_loader_sizes.argtypes = [vp, vp, vp, vp]
+        L.ref_loader_copy.argtypes = [vp] + [vp] * 8
+        L.ref_experiment_run.argtypes = [cp, i32, i32, i32, vp, vp, vp, vp]
         _LIB = L
     return _LIB
 
@@ -54,11 +64,12 @@ def lib() -> C.CDLL:
 def source_hashes() -> dict:
     """{reference file: sha256} as recorded in the generated header (what libref.so was made from)."""
     out = {}
-    with open(HEADER_PATH) as f:
-        for line in f:
-            if line.startswith("// source: "):
-                _, _, rel, _, h = line.split()
-                out[rel] = h
+    for path in HEADER_PATHS:
+        with open(path) as f:
+            for line in f:
+                if line.startswith("// source: "):
+                    _, _, rel, _, h = line.split()
+                    out[rel] = h
     return out
 
 
@@ -141,3 +152,63 @@ class ReferenceGraph:
         if cnt < 0:
             raise RuntimeError(f"ref_recommend rc={cnt}")
         return ids[:cnt].copy(), sc[:cnt].copy()
+
+
+# ---------------------------------------------------------------------------------------------- the callers
+TABLES = {"follow": ("source", "target"), "tweet": ("id", "author"), "retweet": ("user", "tweet"), "quote": ("user", "tweet"),
+          "favorite": ("user", "tweet"), "mention": ("source", "target")}
+
+
+class ReferenceDb:
+    """The tables of one ego network (schema of SQLiteAdapter.cs:27-125), handed to the reference's DataLoader in rowid order.
+    `path` plays the role of the *.sqlite path: its file name is the ego user's id (DataLoader.cs:32)."""
+
+    def __init__(self, path: str, tables: dict):
+        self.path = path.encode()
+        assert lib().ref_db_reset(self.path) == 0
+        for name, rows in tables.items():
+            assert name in TABLES, name
+            a = np.ascontiguousarray([r[0] for r in rows], np.int64)
+            b = np.ascontiguousarray([r[1] for r in rows], np.int64)
+            assert lib().ref_db_add(self.path, name.encode(), _p(a), _p(b), len(a)) == 0
+
+    @classmethod
+    def from_sqlite(cls, db_path: str) -> "ReferenceDb":
+        import sqlite3
+        conn = sqlite3.connect(db_path)
+        tables = {name: conn.execute(f"SELECT {a}, {b} FROM {name} ORDER BY rowid").fetchall() for name, (a, b) in TABLES.items()}
+        conn.close()
+        return cls(db_path, tables)
+
+    def validation(self, n_folds: int):
+        """DataLoader.checkEgoNetworkValidation -> (valid, cntLikes, cntFriends)."""
+        v, l, f = C.c_int32(), C.c_int32(), C.c_int32()
+        assert lib().ref_loader_validation(self.path, int(n_folds), C.byref(v), C.byref(l), C.byref(f)) == 0
+        return bool(v.value), l.value, f.value
+
+    def load(self, n_folds: int, methodology: int, fold: int) -> dict:
+        """`new DataLoader(path, nFolds).graphConfiguration(methodology, fold)` -> allNodes / allLinks flattened + testSet."""
+        h = lib().ref_loader_run(self.path, int(n_folds), int(methodology), int(fold))
+        if not h:
+            raise RuntimeError("the reference's DataLoader threw")
+        try:
+            n, e, t = C.c_int32(), C.c_int64(), C.c_int64()
+            lib().ref_loader_sizes(h, C.byref(n), C.byref(e), C.byref(t))
+            out = dict(node_id=np.empty(n.value, np.int64), node_type=np.empty(n.value, np.int32), has_entry=np.empty(n.value, np.int8),
+                       src=np.empty(e.value, np.int32), dst=np.empty(e.value, np.int32), etype=np.empty(e.value, np.int32),
+                       w=np.empty(e.value, np.float64), test_ids=np.empty(t.value, np.int64))
+            lib().ref_loader_copy(h, *[_p(out[k]) for k in ("node_id", "node_type", "has_entry", "src", "dst", "etype", "w", "test_ids")])
+            return out
+        finally:
+            lib().ref_loader_destroy(h)
+
+    def experiment(self, n_folds: int, n_iter: int, methodology: int):
+        """The k-fold loop of Experiment.runKFoldCrossValidation -> dict(valid, hit, avg_precision_sum, cnt_likes)."""
+        hit, ap, likes, valid = C.c_double(), C.c_double(), C.c_int32(), C.c_int32()
+        rc = lib().ref_experiment_run(self.path, int(n_folds), int(n_iter), int(methodology), C.byref(hit), C.byref(ap),
+                                      C.byref(likes), C.byref(valid))
+        if rc == REF_E_BADSEED:
+            raise KeyError("the ego user has no links (KeyNotFoundException, Recommender.cs:21)")
+        if rc < 0:
+            raise RuntimeError(f"ref_experiment_run rc={rc}")
+        return dict(valid=bool(valid.value), hit=hit.value, avg_precision_sum=ap.value, cnt_likes=likes.value)

@@ -1,18 +1,24 @@
 // TEST INFRASTRUCTURE ONLY -- the product path (recommendersystems_b200/, librwr_b200.so) never links, loads or calls this.
 //
 // C ABI over the reference's OWN classes: oracle/_ref/reference_rwr.hpp is Recommenders/RWRBased/{Graph,Model,Recommender}.cs
-// as oracle/cs2cpp.py respells them for a C++ compiler (built from the sources where they lie under /root/reference; the
-// header is git-ignored and never committed).  This file only does what the reference's callers do
+// and oracle/_ref/reference_experiment.hpp is TweetRecommender/DataLoader.cs + the k-fold loop of Experiment.cs, as
+// oracle/cs2cpp.py respells them for a C++ compiler (built from the sources where they lie under /root/reference; the
+// headers are git-ignored and never committed).  This file only does what the reference's callers do
 // (TweetRecommender/DataLoader.cs:60-77 fills `allNodes` / `allLinks`, Experiment.cs:104-109 builds the graph and asks for a
-// recommendation) and copies the results out; it contains no arithmetic of the path.
+// recommendation, Experiment.cs:61-66 sets up the result dictionary) and copies the results out; it contains no arithmetic
+// of the path.
 //
 // Build: `make -C oracle ref`  ->  oracle/_ref/libref.so   (g++ -O2 -std=c++17 -ffp-contract=off -fno-fast-math)
 #include <cstdint>
 #include <cstring>
 
 #include "_ref/reference_rwr.hpp"
+#include "_ref/reference_experiment.hpp"
 
 using namespace Recommenders_RWRBased;
+using TweetRecommender::DataLoader;
+using TweetRecommender::EvaluationMetric;
+using TweetRecommender::Methodology;
 
 namespace {
 
@@ -147,6 +153,114 @@ int64_t ref_recommend(void* h, int32_t seed, float damping, int32_t n_iter, int3
         for (int64_t i = 0; i < count; i++) { ids[i] = list[i].Key; scores[i] = list[i].Value; }
     });
     return rc == REF_OK ? count : rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The callers: DataLoader over in-memory tables, and the k-fold loop of Experiment.runKFoldCrossValidation.
+
+// the tables of one ego network's database, registered under `path` (`<ego user id>.sqlite`, DataLoader.cs:32)
+int ref_db_reset(const char* path) {
+    bcl::mem_dbs()[path] = bcl::MemDb();
+    return REF_OK;
+}
+
+// rows (a[i], b[i]) appended to `table` in order: follow(source, target), tweet(id, author), retweet / quote / favorite(user, tweet),
+// mention(source, target)
+int ref_db_add(const char* path, const char* table, const int64_t* a, const int64_t* b, int64_t n) {
+    auto it = bcl::mem_dbs().find(path);
+    if (it == bcl::mem_dbs().end()) return REF_E_INVALID;
+    auto& rows = it->second.tables[table];
+    for (int64_t i = 0; i < n; i++) rows.emplace_back((long long)a[i], (long long)b[i]);
+    return REF_OK;
+}
+
+struct RefLoader {
+    DataLoader* loader = nullptr;
+    int32_t n = 0;
+    int64_t e = 0;
+    ~RefLoader() { delete loader; }
+};
+
+// checkEgoNetworkValidation (DataLoader.cs:79-92) and the two counts it is made of
+int ref_loader_validation(const char* path, int32_t n_folds, int32_t* valid, int32_t* cnt_likes, int32_t* cnt_friends) {
+    try {
+        DataLoader loader(path, n_folds);
+        *cnt_likes = loader.getLikeCountOfEgoUser();
+        *cnt_friends = loader.getFriendsCountOfEgoUser();
+        *valid = loader.checkEgoNetworkValidation() ? 1 : 0;
+        return REF_OK;
+    } catch (...) {
+        return REF_E_INVALID;
+    }
+}
+
+// `new DataLoader(path, nFolds)` + `graphConfiguration(methodology, fold)` (Experiment.cs:71, :77)
+void* ref_loader_run(const char* path, int32_t n_folds, int32_t methodology, int32_t fold) {
+    RefLoader* h = new RefLoader();
+    try {
+        h->loader = new DataLoader(path, n_folds);
+        h->loader->graphConfiguration((Methodology)methodology, fold);
+        h->n = h->loader->allNodes.Count();
+        for (int32_t i = 0; i < h->n; i++)
+            if (h->loader->allLinks.ContainsKey(i)) h->e += h->loader->allLinks[i].Count();
+        return h;
+    } catch (...) {
+        delete h;
+        return nullptr;
+    }
+}
+
+void ref_loader_destroy(void* h) { delete (RefLoader*)h; }
+
+void ref_loader_sizes(void* hv, int32_t* n_nodes, int64_t* n_links, int64_t* n_test) {
+    RefLoader* h = (RefLoader*)hv;
+    *n_nodes = h->n;
+    *n_links = h->e;
+    *n_test = h->loader->testSet.Count();
+}
+
+// allNodes / allLinks flattened as `for i in 0..N-1: foreach l in allLinks[i]`, has_entry[i] = allLinks.ContainsKey(i),
+// testSet in its enumeration order
+void ref_loader_copy(void* hv, int64_t* node_id, int32_t* node_type, int8_t* has_entry, int32_t* src, int32_t* dst, int32_t* etype,
+                     double* w, int64_t* test_ids) {
+    RefLoader* h = (RefLoader*)hv;
+    int64_t p = 0;
+    for (int32_t i = 0; i < h->n; i++) {
+        node_id[i] = h->loader->allNodes[i].id;
+        node_type[i] = (int32_t)h->loader->allNodes[i].type;
+        has_entry[i] = h->loader->allLinks.ContainsKey(i) ? 1 : 0;
+        if (!has_entry[i]) continue;
+        for (ForwardLink l : h->loader->allLinks[i]) {
+            src[p] = i; dst[p] = l.targetNode; etype[p] = (int32_t)l.type; w[p] = l.weight;
+            p++;
+        }
+    }
+    int64_t t = 0;
+    for (long long id : h->loader->testSet) test_ids[t++] = id;
+}
+
+// Experiment.runKFoldCrossValidation for one database and one methodology: the result dictionary as Experiment.cs:61-66 sets it
+// up, then the reference's own k-fold loop (runFolds).  Out: finalResult[HIT], finalResult[AVGPRECISION] (the SUM over the folds;
+// the result row divides it by nFolds, Experiment.cs:150), cntLikes; valid = 0 when checkEgoNetworkValidation made it return.
+int ref_experiment_run(const char* path, int32_t n_folds, int32_t n_iterations, int32_t methodology, double* hit,
+                       double* avg_precision_sum, int32_t* cnt_likes, int32_t* valid) {
+    try {
+        Dictionary<EvaluationMetric, double> finalResult;
+        finalResult.Add(EvaluationMetric::HIT, 0.0);                       // foreach (metric in Enum.GetValues(..)) finalResult.Add(metric, 0d)
+        finalResult.Add(EvaluationMetric::AVGPRECISION, 0.0);
+        List<EvaluationMetric> metrics;                                    // new List<EvaluationMetric>(finalResult.Keys)
+        for (EvaluationMetric m : finalResult.Keys()) metrics.Add(m);
+        int cntLikes = 0;
+        *valid = TweetRecommender::runFolds(path, n_folds, n_iterations, (Methodology)methodology, finalResult, metrics, cntLikes) ? 1 : 0;
+        *hit = finalResult[EvaluationMetric::HIT];
+        *avg_precision_sum = finalResult[EvaluationMetric::AVGPRECISION];
+        *cnt_likes = cntLikes;
+        return REF_OK;
+    } catch (const bcl::KeyNotFoundException&) {
+        return REF_E_BADSEED;                                              // the ego user has no `edges` entry (Recommender.cs:21)
+    } catch (...) {
+        return REF_E_INVALID;
+    }
 }
 
 }  // extern "C"

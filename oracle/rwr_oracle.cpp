@@ -23,8 +23,11 @@
 // Two iteration forms:
 //   literal   -- the O(N^2) restart loops exactly as written (Model.cs:92-93, :96-97);
 //   collapsed -- `next[seed] += rank_restart` at the same point of the i-loop.  For a one-hot
-//                restart vector every other addend is `x * 0.0 == +0.0` and `y + 0.0 == y`
-//                (all y >= +0), so the two forms are bit-identical; the tests assert it.
+//                restart vector every other addend is `x * 0.0 == +-0.0` and `y + 0.0 == y`, so the
+//                two forms are bit-identical while x is finite; a NaN or Inf rank (a row whose
+//                weights sum to 0, Graph.cs:81) makes `x * 0.0` NaN for EVERY node -- the whole
+//                next vector is NaN in the reference -- and the collapsed form then runs the
+//                literal loop for that source.  The tests assert the identity, NaN cases included.
 //
 // Also here: the CPU side of the deterministic synthetic graph generator (this repo's own spec,
 // include/rwr_b200.h `rwr_synth_spec`; it replaces DataLoader.cs:256-436) written independently of
@@ -142,14 +145,14 @@ struct Model {
                 for (int64_t w = b; w < e; w++)
                     nextRank[col[w]] += rank_randomWalk * val[w];               // :87
                 double rank_restart = rank[i] - rank_randomWalk;                // :91
-                if (collapse) {
+                if (collapse && std::isfinite(rank_restart)) {
                     nextRank[seed] += rank_restart * 1.0;
-                } else if (!skip_restart) {
+                } else if (!skip_restart) {                                     // literal form, or a NaN / Inf that `* 0` spreads
                     for (int r = 0; r < nNodes; r++)
                         nextRank[r] += rank_restart * restart[r];               // :93
                 }
             } else {
-                if (collapse) {
+                if (collapse && std::isfinite(rank[i])) {
                     nextRank[seed] += rank[i] * 1.0;
                 } else if (!skip_restart) {
                     for (int r = 0; r < nNodes; r++)

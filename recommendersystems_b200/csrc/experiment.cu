@@ -5,7 +5,12 @@
 //   N2  rwr_graph_hold_out      DataLoader.splitLikeHistory (DataLoader.cs:122-140) + the LIKE links of the test fold that
 //                               never reach `edges` (DataLoader.cs:287-298), for many test users of one graph at once:
 //                               candidate likes -> stable LSD sort by (user, tweet id) -> fold window -> both directions of
-//                               every held-out like leave the raw link list (stable compaction, insertion order kept)
+//                               every held-out like leave the raw link list (stable compaction, insertion order kept).
+//                               A held-out tweet that no LIKE link reaches any more is no node of the reference's graph at
+//                               all (DataLoader creates tweet nodes while it walks somebody's likes, :291-303, and
+//                               addAuthorship skips tweets that are not nodes, :355-356): its remaining links leave too and
+//                               its node type becomes UNDEFINED, so it is no candidate (Recommender.cs:29) and never a hit
+//                               (Experiment.cs:124); the node index itself stays, indices do not shift
 // The evaluation itself (N1, Experiment.cs:121-128) lives next to the top-k kernels in select.cu.
 #include <algorithm>
 #include <vector>
@@ -180,6 +185,37 @@ __global__ void k_ho_reverse(const int32_t* __restrict__ raw_src, const int32_t*
     if (hs_has(tab, mask, ((u64)(u32)s << 32) | (u64)(u32)raw_dst[e])) removed[e] = 1;
 }
 
+// ---- held-out tweets nobody likes any more (see the header) ----------------------------------------------------------
+// remaining LIKE links into ITEM nodes, per target
+__global__ void k_ho_like_in(const int32_t* __restrict__ raw_dst, const u8* __restrict__ raw_type, const u8* __restrict__ node_type,
+                             int n, size_t e0, const u8* __restrict__ removed, u32* __restrict__ like_in) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e0 || removed[e]) return;
+    if (is_like_of_item(raw_type[e], raw_dst[e], node_type, n)) atomicAdd(&like_in[raw_dst[e]], 1u);
+}
+// a removed LIKE link into an ITEM is the u -> t half of a held-out like: t is an orphan when nothing is left in like_in[t]
+__global__ void k_ho_orphans(const int32_t* __restrict__ raw_dst, const u8* __restrict__ raw_type, const u8* __restrict__ node_type,
+                             int n, size_t e0, const u8* __restrict__ removed, const u32* __restrict__ like_in,
+                             u8* __restrict__ orphan, u32* __restrict__ any) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e0 || !removed[e]) return;
+    if (is_like_of_item(raw_type[e], raw_dst[e], node_type, n) && like_in[raw_dst[e]] == 0) {
+        orphan[raw_dst[e]] = 1;
+        *any = 1u;
+    }
+}
+__global__ void k_ho_drop_orphan_links(const int32_t* __restrict__ raw_src, const int32_t* __restrict__ raw_dst, int n, size_t e0,
+                                       const u8* __restrict__ orphan, u8* __restrict__ removed) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= e0) return;
+    const int32_t s = raw_src[e], d = raw_dst[e];
+    if (((u32)s < (u32)n && orphan[s]) || ((u32)d < (u32)n && orphan[d])) removed[e] = 1;
+}
+__global__ void k_ho_retype_orphans(const u8* __restrict__ orphan, int n, u8* __restrict__ node_type) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n && orphan[j]) node_type[j] = RWR_NODE_UNDEFINED;
+}
+
 __global__ void k_ho_keep_flags(const u8* __restrict__ removed, size_t e0, u32* __restrict__ flags) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e < e0) flags[e] = removed[e] ? 0u : 1u;
@@ -296,6 +332,30 @@ extern "C" int rwr_graph_hold_out(rwr_graph* g, const int32_t* users, int32_t n_
     KERNEL_CHECK();
     g->held_ids.resize(held);
     CUDA_CHECK(cudaMemcpyAsync(g->held_ids.data(), d_test.p, held * 8, cudaMemcpyDeviceToHost, st));
+
+    // ---- held-out tweets that no LIKE link reaches any more leave the graph (their other links, their candidacy)
+    {
+        DevBuf<u32> like_in, any;
+        DevBuf<u8> orphan;
+        like_in.alloc((size_t)n); any.alloc(1); orphan.alloc((size_t)n);
+        CUDA_CHECK(cudaMemsetAsync(like_in.p, 0, (size_t)n * sizeof(u32), st));
+        CUDA_CHECK(cudaMemsetAsync(any.p, 0, sizeof(u32), st));
+        CUDA_CHECK(cudaMemsetAsync(orphan.p, 0, (size_t)n, st));
+        k_ho_like_in<<<grid_of(e0), 256, 0, st>>>(g->raw_dst.p, g->raw_type.p, g->node_type.p, n, e0, removed.p, like_in.p);
+        k_ho_orphans<<<grid_of(e0), 256, 0, st>>>(g->raw_dst.p, g->raw_type.p, g->node_type.p, n, e0, removed.p, like_in.p, orphan.p,
+                                                 any.p);
+        KERNEL_CHECK();
+        u32 h_any = 0;
+        CUDA_CHECK(cudaMemcpyAsync(&h_any, any.p, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        CUDA_CHECK(cudaStreamSynchronize(st));
+        if (h_any) {
+            k_ho_drop_orphan_links<<<grid_of(e0), 256, 0, st>>>(g->raw_src.p, g->raw_dst.p, n, e0, orphan.p, removed.p);
+            k_ho_retype_orphans<<<grid_of((size_t)n), 256, 0, st>>>(orphan.p, n, g->node_type.p);
+            KERNEL_CHECK();
+            g->pool.launches += 2;
+        }
+        g->pool.launches += 2;
+    }
 
     // ---- stable compaction of `edges`
     DevBuf<u32> pos;

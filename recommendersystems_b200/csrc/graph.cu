@@ -67,12 +67,33 @@ __global__ void k_lower_bounds(const KeyT* __restrict__ keys, size_t e, int32_t 
 // `mask`: bit t set = links of EdgeType t count as UNDEFINED (the methodology switches of Experiment.cs:84-101, which
 // retype FRIENDSHIP links to UNDEFINED before buildGraph(), as one option instead of a rewrite of the link list)
 __device__ __forceinline__ bool link_is_explicit(u8 t, u32 mask) { return t != RWR_EDGE_UNDEFINED && !(t < 32 && ((mask >> t) & 1u)); }
+__device__ __forceinline__ bool type_in(u8 t, u32 mask) { return t < 32 && ((mask >> t) & 1u); }
 
-__global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __restrict__ dst, size_t e0, int32_t n,
-                                 u32 mask, u32* __restrict__ flags, int* bad) {
+// rwr_opts.zero_weight_type_mask (MENTION under methodology 15): DataLoader.addMentionCount2 gives a member mention links only
+// when `allLinks` already holds an entry for it (DataLoader.cs:403-405) -- a member whose other relations were not loaded gets
+// none and stays a dangling row, it does NOT become a row of zero weights (0 / 0 = NaN).  Hence: a link of a zero-weight type
+// is in the matrix only if its source has an explicit link of another type (`carrier[source]`, null when no such type is set).
+__device__ __forceinline__ bool link_in_matrix(u8 t, const int32_t* __restrict__ src, size_t i, u32 mask, u32 zero_mask,
+                                               const u8* __restrict__ carrier) {
+    if (!link_is_explicit(t, mask)) return false;
+    if (carrier && type_in(t, zero_mask)) return carrier[src[i]] != 0;       // (src is only read on this path)
+    return true;
+}
+__global__ void k_carrier_flags(const u8* __restrict__ type, const int32_t* __restrict__ src, size_t e0, int32_t n, u32 mask,
+                                u32 zero_mask, u8* __restrict__ carrier) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < e0 && link_is_explicit(type[i], mask) && !type_in(type[i], zero_mask)) {
+        const int32_t s = src[i];
+        if (s >= 0 && s < n) carrier[s] = 1;
+    }
+}
+
+__global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __restrict__ src, const int32_t* __restrict__ dst,
+                                 size_t e0, int32_t n, u32 mask, u32 zero_mask, const u8* __restrict__ carrier,
+                                 u32* __restrict__ flags, int* bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e0) {
-        u32 f = link_is_explicit(type[i], mask);
+        u32 f = link_in_matrix(type[i], src, i, mask, zero_mask, carrier);
         if (f) {
             int32_t d = dst[i];
             if (d < 0 || d >= n) *bad = 1;
@@ -85,23 +106,24 @@ __global__ void k_explicit_flags(const u8* __restrict__ type, const int32_t* __r
 // `zero_mask`: links of these types keep their slot with weight 0.0 (rwr_opts.zero_weight_type_mask)
 __global__ void k_compact(const u8* __restrict__ type, const u32* __restrict__ pos, const int32_t* __restrict__ src,
                           const int32_t* __restrict__ dst, const double* __restrict__ w, size_t e0, u32 mask, u32 zero_mask,
-                          int32_t* __restrict__ src_of, int32_t* __restrict__ col, double* __restrict__ wv) {
+                          const u8* __restrict__ carrier, int32_t* __restrict__ src_of, int32_t* __restrict__ col,
+                          double* __restrict__ wv) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < e0) {
         const u8 t = type[i];
-        if (!link_is_explicit(t, mask)) return;
+        if (!link_in_matrix(t, src, i, mask, zero_mask, carrier)) return;
         u32 p = pos[i];
         src_of[p] = src[i];
         col[p] = dst[i];
-        wv[p] = (t < 32 && ((zero_mask >> t) & 1u)) ? 0.0 : w[i];
+        wv[p] = type_in(t, zero_mask) ? 0.0 : w[i];
     }
 }
 
 // `graph[i][k].type`: the types of the explicit links in CSR order
-__global__ void k_compact_types(const u8* __restrict__ type, const u32* __restrict__ pos, size_t e0, u32 mask,
-                                int32_t* __restrict__ out) {
+__global__ void k_compact_types(const u8* __restrict__ type, const int32_t* __restrict__ src, const u32* __restrict__ pos, size_t e0,
+                                u32 mask, u32 zero_mask, const u8* __restrict__ carrier, int32_t* __restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < e0 && link_is_explicit(type[i], mask)) out[pos[i]] = (int32_t)type[i];
+    if (i < e0 && link_in_matrix(type[i], src, i, mask, zero_mask, carrier)) out[pos[i]] = (int32_t)type[i];
 }
 
 __global__ void k_row_ptr_from_pos(const u32* __restrict__ raw_ptr, const u32* __restrict__ pos, size_t e0, u32 nnz,
@@ -518,8 +540,17 @@ static void graph_build_impl(rwr_graph* g) {
     DevBuf<u32> pos, total;
     pos.alloc(e0);
     total.alloc(1);
+    DevBuf<u8> carrier;                    // sources that hold an explicit link of a type outside zero_weight_type_mask
+    const u32 zero_mask = (u32)g->opts.zero_weight_type_mask;
     if (e0) {
-        k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, n, (u32)g->opts.undefined_type_mask, pos.p, bad.p);
+        if (zero_mask) {
+            carrier.alloc((size_t)std::max(n, 1));
+            CUDA_CHECK(cudaMemsetAsync(carrier.p, 0, (size_t)std::max(n, 1), st));
+            k_carrier_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_src.p, e0, n, (u32)g->opts.undefined_type_mask, zero_mask,
+                                                         carrier.p);
+        }
+        k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_src.p, g->raw_dst.p, e0, n, (u32)g->opts.undefined_type_mask,
+                                                      zero_mask, carrier.p, pos.p, bad.p);
         KERNEL_CHECK();
     }
     prim::exclusive_scan<u32>(pos.p, pos.p, e0, total.p, st, &g->pool);
@@ -548,7 +579,7 @@ static void graph_build_impl(rwr_graph* g) {
         g->src_of_own.alloc(nnz, &g->pool);
         wv_own.alloc(nnz);
         k_compact<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, g->raw_src.p, g->raw_dst.p, g->raw_w.p, e0,
-                                                (u32)g->opts.undefined_type_mask, (u32)g->opts.zero_weight_type_mask,
+                                                (u32)g->opts.undefined_type_mask, zero_mask, carrier.p,
                                                 g->src_of_own.p, g->col_own.p, wv_own.p);
         k_row_ptr_from_pos<<<grid_for((size_t)n + 1), 256, 0, st>>>(g->raw_ptr.p, pos.p, e0, (u32)nnz, n, g->row_ptr_own.p);
         KERNEL_CHECK();
@@ -559,6 +590,7 @@ static void graph_build_impl(rwr_graph* g) {
     }
     CUDA_CHECK(cudaStreamSynchronize(st));
     pos.release();
+    carrier.release();
 
     trace.mark("K1-K3 flags/scan/compact");
     // ---- K4: row sums (sequential order), normalisation
@@ -1050,10 +1082,20 @@ int rwr_graph_get_csr_types(rwr_graph* g, int32_t* etype) {
     DevBuf<int> bad;
     DevBuf<int32_t> out;
     pos.alloc(e0); bad.alloc(1); out.alloc(nnz);
-    k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_dst.p, e0, g->n, (u32)g->opts.undefined_type_mask, pos.p, bad.p);
+    DevBuf<u8> carrier;
+    const u32 zero_mask = (u32)g->opts.zero_weight_type_mask;
+    if (zero_mask) {
+        carrier.alloc((size_t)std::max(g->n, 1));
+        CUDA_CHECK(cudaMemsetAsync(carrier.p, 0, (size_t)std::max(g->n, 1), st));
+        k_carrier_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_src.p, e0, g->n, (u32)g->opts.undefined_type_mask, zero_mask,
+                                                     carrier.p);
+    }
+    k_explicit_flags<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_src.p, g->raw_dst.p, e0, g->n, (u32)g->opts.undefined_type_mask,
+                                                  zero_mask, carrier.p, pos.p, bad.p);
     KERNEL_CHECK();
     prim::exclusive_scan<u32>(pos.p, pos.p, e0, nullptr, st, &g->pool);
-    k_compact_types<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, pos.p, e0, (u32)g->opts.undefined_type_mask, out.p);
+    k_compact_types<<<grid_for(e0), 256, 0, st>>>(g->raw_type.p, g->raw_src.p, pos.p, e0, (u32)g->opts.undefined_type_mask, zero_mask,
+                                                 carrier.p, out.p);
     KERNEL_CHECK();
     CUDA_CHECK(cudaMemcpyAsync(etype, out.p, nnz * 4, cudaMemcpyDeviceToHost, st));
     CUDA_CHECK(cudaStreamSynchronize(st));

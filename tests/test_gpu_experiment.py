@@ -39,9 +39,13 @@ def test_hold_out_matches_the_restatement(n_folds, fold):
     g = from_links(full)
     test = g.hold_out(users, n_folds, fold)
     got = g.export_links()
-    for k in ("src", "dst", "etype"):
+    for k in ("src", "dst", "etype", "node_type"):
         assert np.array_equal(got[k], want_links[k]), k
     assert np.array_equal(bits(got["w"]), bits(want_links["w"]))
+    # held-out tweets that nobody likes any more: no node of the reference's graph (retyped UNDEFINED here, their links gone)
+    orphans = np.flatnonzero(got["node_type"] != full["node_type"])
+    assert len(orphans) >= 10 and (got["node_type"][orphans] == 0).all() and (full["node_type"][orphans] == 2).all()
+    assert not np.isin(got["src"], orphans).any() and not np.isin(got["dst"], orphans).any()
     for u in users:
         assert test[u].tolist() == want_test[u].tolist(), u
     # the edited graph builds like any other, bit-exact CSR against the oracle on the restated links
@@ -233,10 +237,37 @@ def test_sqlite_ego_network_through_the_fold_loop(tmp_path, methodology):
     assert net.like_count() >= 60 and (links["etype"] == R.MENTION).sum() > 10 and (links["node_type"] == 3).sum() > 10
     out = X.run_k_fold(links, methodology, n_folds=4, n_iter=12, ego=0, validate=False)
     hits, sum_ap, folds = R.run_k_fold(links, methodology, 4, 12, 0)
-    assert out["hits"] == int(hits) == net.like_count()                  # every held-out like is found somewhere in the full ranking
+    assert out["hits"] == int(hits) and 0 < out["hits"] < net.like_count()  # held-out tweets nobody else likes are no nodes: no hit
     assert [f["hits"] for f in out["folds"]] == [f[1] for f in folds]
     assert abs(out["map"] - sum_ap / 4) <= 1e-12
     assert out["row"].split("\t")[:4] == ["1000", str(methodology), "4", "12"]
+
+
+@pytest.mark.parametrize("methodology", [8, 15, 4, 0])
+def test_k_fold_against_the_reference_itself(tmp_path, methodology):
+    """The whole chain on the device -- SQLite ingest (N4), methodology masks (N3), hold-out (N2), RWR, evaluation (N1) -- against
+    the reference's OWN DataLoader and k-fold loop (DataLoader.cs + Experiment.cs compiled from their sources, oracle/_ref):
+    HIT identical, AVGPRECISION to 1e-12, the result.dat row.  Without the prebuilt library: against the restated loop."""
+    import random
+    import ego_db
+    import ref as RF
+    from recommendersystems_b200.ingest import load_ego_network
+    tables = ego_db.random_tables(random.Random(32))      # 15 mention links lose their carrier under methodology 15
+    db = ego_db.write_sqlite(str(tmp_path / "1000.sqlite"), tables)
+    links, net = load_ego_network(db)
+    assert net.is_valid(10)
+    out = X.run_k_fold(links, methodology, n_folds=10, n_iter=6, ego=0)
+    if RF.available(build=False):
+        ref = RF.ReferenceDb(db, tables).experiment(10, 6, methodology)
+        want_hits, want_ap, likes = ref["hit"], ref["avg_precision_sum"], ref["cnt_likes"]
+        assert ref["valid"]
+    else:
+        want_hits, want_ap, _ = R.run_k_fold(links, methodology, 10, 6, 0)
+        likes = net.like_count()
+    assert out["hits"] == int(want_hits) and out["hits"] < likes == out["cnt_likes"]
+    assert abs(out["map"] - want_ap / 10) <= 1e-12
+    tok = out["row"].split("\t")
+    assert tok[:6] == ["1000", str(methodology), "10", "6", str(int(want_hits)), str(likes)] and abs(float(tok[6]) - want_ap / 10) <= 1e-14
 
 
 def test_evaluate_users_with_thousands_of_test_items():

@@ -7,7 +7,10 @@ from where they lie under /root/reference after oracle/cs2cpp.py has respelt the
   * where libref.so exists, the transliterated reference must reproduce every committed golden vector bit for bit, and the
     hand-written oracle (literal and collapsed forms) must agree with it bit for bit on random graphs with the corner cases
     of SURVEY 8(a): dangling rows, multi-edges, UNDEFINED-only rows, fractional weights, zero weight sums (NaN / Inf),
-    the exceptions of the drop-in boundary, and on the C1-shaped synthetic graph.
+    the exceptions of the drop-in boundary, and on the C1-shaped synthetic graph;
+  * the callers' rows: the reference's own DataLoader (over in-memory tables instead of System.Data.SQLite)
+    and the k-fold loop of Experiment.runKFoldCrossValidation against the product's ingest + the restated hold-out,
+    methodology table and evaluation loop -- node and link order, test sets, HIT and AVGPRECISION of all 16 methodologies.
 """
 import hashlib
 import os
@@ -229,9 +232,7 @@ def test_oracle_matches_the_reference_on_random_graphs(case):
         for it in (0, 1, 2, 7, 20):
             want, _ = rg.run(seed, c, n_iter=it)
             for literal in (True, False):
-                got, _ = og.run(seed, c, n_iter=it, literal=literal)
-                if poisoned and not literal:
-                    continue        # the collapsed form drops the `x * 0` addends: identical unless x is NaN / Inf (oracle header)
+                got, _ = og.run(seed, c, n_iter=it, literal=literal)       # NaN / Inf rows: `x * 0` poisons every node, in both forms
                 assert np.array_equal(bits(got), bits(want)), (case, seed, it, literal)
         if not poisoned:
             for thr in (1e-3, 1e-9):
@@ -246,7 +247,7 @@ def test_oracle_matches_the_reference_on_random_graphs(case):
             continue
         for top in (None, 1, 10, 0, -3):
             wi, ws = rg.recommend(seed, 0.15, 5, top_n=top)
-            gi, gs = og.recommend(seed, 0.15, 5, top_n=top, literal=poisoned)
+            gi, gs = og.recommend(seed, 0.15, 5, top_n=top)
             assert wi.tolist() == gi.tolist() and np.array_equal(bits(ws), bits(gs)), (case, seed, top)
     u_want, _ = rg.run(-1, c, n_iter=4)                    # the uniform-restart constructor (Model.cs:14-31)
     u_got, _ = og.run(-1, c, n_iter=4, literal=True)
@@ -306,9 +307,93 @@ def test_reference_fixture():
     assert MG.generate(O.OracleGraph) == want
     if HAVE_REF:
         assert MG.generate(RF.ReferenceGraph) == want
-        assert made_from == RF.source_hashes()          # the fixture and libref.so come from the same reference files
+        now = RF.source_hashes()                        # the fixture and libref.so come from the same reference files
+        assert all(now[rel] == h for rel, h in made_from.items()) and len(made_from) == 3
 
 
 def json_load(f):
     import json
     return json.load(f)
+
+
+# ---------------------------------------------------------------------------------------------- the callers: DataLoader, Experiment
+def _ego(tmp_path, seed, **kw):
+    import ego_db
+    from recommendersystems_b200.ingest import load_ego_network
+    tables = ego_db.random_tables(random.Random(seed), **kw)
+    db = ego_db.write_sqlite(str(tmp_path / "1000.sqlite"), tables)
+    links, net = load_ego_network(db)                                   # the product's ingest (N4), every relation loaded
+    return RF.ReferenceDb(db, tables), links, net
+
+
+def _by_id(L):
+    """{source id: [(target id, type, weight) in insertion order]} and {node id: type} of a flattened link list."""
+    ids = np.asarray(L["node_id"])
+    per = {}
+    for s, d, t, w in zip(np.asarray(L["src"]).tolist(), np.asarray(L["dst"]).tolist(), np.asarray(L["etype"]).tolist(),
+                          np.asarray(L["w"]).tolist()):
+        per.setdefault(int(ids[s]), []).append((int(ids[d]), t, w))
+    return per, {int(i): int(t) for i, t in zip(ids, np.asarray(L["node_type"]))}
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", [11, 12])
+def test_k_fold_loop_matches_the_reference(tmp_path, seed):
+    """Experiment.runKFoldCrossValidation (its own loop, compiled from Experiment.cs) against ingest + restated fold loop:
+    HIT identical, AVGPRECISION to 1e-12, for every methodology."""
+    import experiment_ref as R
+    from recommendersystems_b200.experiment import result_row
+    rdb, links, net = _ego(tmp_path, seed)
+    n_folds, n_iter = 10, 6
+    assert rdb.validation(n_folds) == (True, net.like_count(), net.friends_count()) and net.is_valid(n_folds)
+    for m in range(16):
+        ref = rdb.experiment(n_folds, n_iter, m)
+        hits, sum_ap, folds = R.run_k_fold(links, m, n_folds, n_iter)
+        assert ref["valid"] and ref["cnt_likes"] == net.like_count()
+        assert ref["hit"] == hits and hits < net.like_count(), m          # some held-out tweets are liked by nobody else: no hit
+        assert abs(ref["avg_precision_sum"] - sum_ap) <= 1e-12 * max(1.0, sum_ap), m
+        row = result_row(net.ego_id, m, n_folds, n_iter, hits, net.like_count(), sum_ap).split("\t")
+        assert row[:6] == ["1000", str(m), "10", "6", str(int(ref["hit"])), str(ref["cnt_likes"])]      # Experiment.cs:144-152
+        assert abs(float(row[6]) - ref["avg_precision_sum"] / n_folds) <= 1e-14
+
+
+@needs_ref
+def test_invalid_ego_network_returns_like_the_reference(tmp_path):
+    rdb, links, net = _ego(tmp_path, 5, n_friends=20, ego_likes=60)         # < 50 friends: Experiment.cs:72-74 returns
+    assert rdb.validation(10) == (False, net.like_count(), net.friends_count()) and not net.is_valid(10)
+    assert rdb.experiment(10, 3, 8)["valid"] is False
+    rdb, links, net = _ego(tmp_path, 6, ego_likes=30)                        # < 50 likes
+    assert rdb.validation(10)[0] is False and not net.is_valid(10)
+    assert rdb.validation(40)[0] is False and rdb.validation(31)[0] is False  # cntLikes < nFolds
+
+
+@needs_ref
+@pytest.mark.parametrize("methodology,fold", [(8, 3), (0, 0), (4, 9), (2, 5), (15, 7), (13, 9), (9, 1)])
+def test_loader_graph_matches_ingest_hold_out_and_masks(tmp_path, methodology, fold):
+    """`new DataLoader(db, 10).graphConfiguration(methodology, fold)` (compiled from DataLoader.cs) against the product's way to
+    the same graph: ONE ingest with every relation, then the fold's hold-out and the methodology's feature set.  Same test
+    set; same nodes, except those the reference never creates (third-party users of an unloaded FOLLOW feature -- isolated
+    here -- and held-out tweets nobody else likes -- isolated and retyped here); the same link list under every source, in
+    the same order, with the same weights (MENTION weights through libm's log on both sides)."""
+    import experiment_ref as R
+    rdb, links, net = _ego(tmp_path, 21)
+    ref = rdb.load(10, methodology, fold)
+    held, test = R.hold_out(links, [0], 10, fold)
+    cfg = R.apply_methodology(held, methodology)
+    if methodology in R.RETYPE_FRIENDSHIP:                                # Experiment.cs:84-101 runs after the loader
+        ref["etype"] = np.where(ref["etype"] == R.FRIENDSHIP, 0, ref["etype"])
+    assert sorted(ref["test_ids"].tolist()) == test[0].tolist() and len(test[0]) == 7
+    a, ta = _by_id(ref)
+    b, tb = _by_id(cfg)
+    assert a == b                                                         # link lists by source id, insertion order, weights
+    assert set(ta) <= set(tb) and all(tb[i] == t for i, t in ta.items())
+    extra = set(tb) - set(ta)
+    assert all(i not in b and not any(i == d for ls in b.values() for (d, _, _) in ls) for i in extra)    # isolated
+    assert all(tb[i] in (0, 3) for i in extra)                            # retyped orphans, unloaded third-party users
+    # DataLoader creates an `edges` entry only by adding a link: "no entry" and "no link" are the same thing, which is what the
+    # flattened input of the C ABI assumes (KeyNotFoundException for a seed without links, Recommender.cs:21)
+    assert np.array_equal(ref["has_entry"].astype(bool), np.bincount(ref["src"], minlength=len(ref["node_id"])) > 0)
+    # node order: the reference numbers members first, then tweets as the likes are walked; ingest does the same with all
+    # of the ego's likes -- the members' prefix is identical
+    k = int((np.asarray(ref["node_type"]) == 1).sum())
+    assert ref["node_id"][:k].tolist() == links["node_id"][:k].tolist()
