@@ -72,7 +72,9 @@ typedef struct rwr_opts {
                            /* still exclude their targets from the recommendation (Recommender.cs:20-24)             */
     int32_t zero_weight_type_mask; /* bit t set: links of EdgeType t stay in the matrix with weight 0.0 -- what               */
                            /* DataLoader.addMentionCount2 produces for MENTION links when the member has no FRIENDSHIP link  */
-                           /* (`nFriendhips * Math.Log(..) / ..`, DataLoader.cs:423-434; Methodology 15)                     */
+                           /* (`nFriendhips * Math.Log(..) / ..`, DataLoader.cs:423-434; Methodology 15) -- and only for a   */
+                           /* source that holds an explicit link of another type: a member without an `allLinks` entry gets  */
+                           /* no mention links (DataLoader.cs:403-405) and stays a dangling row, not a row of NaN weights     */
     int32_t x_blocks;      /* column blocking of the gather vector for graphs whose x is far beyond L2: 0 = auto, 1 = off,    */
                            /* 2..64 = that many blocks                                                       */
     int32_t empty_seed_ok; /* 1: a seed without raw links is accepted by the recommendation calls -- an `edges` entry that   */
@@ -214,7 +216,10 @@ int rwr_methodology_masks(int32_t methodology, int32_t* feature_mask, int32_t* u
  * never enter the graph for the test fold (:287-298), for any number of test users at once.  Call between create and
  * rwr_graph_build.  For each (distinct) user u: likes(u) = targets of u's raw LIKE links that are ITEM nodes, ordered by
  * node id (`likesList.Sort()`); unit = |likes| / n_folds; test fold = positions [unit*fold, fold < n_folds-1 ?
- * unit*(fold+1) : |likes|).  The links u->t and t->u of type LIKE with t in the test fold leave `edges`.  The test sets
+ * unit*(fold+1) : |likes|).  The links u->t and t->u of type LIKE with t in the test fold leave `edges`.  A held-out tweet
+ * that no LIKE link reaches any more is no node of the reference's graph (DataLoader creates tweet nodes while it walks
+ * somebody's likes, :291-303; addAuthorship skips tweets that are no nodes, :355-356): its remaining links leave `edges`
+ * too and its node type becomes RWR_NODE_UNDEFINED -- no candidate, never a hit; node indices do not shift.  The test sets
  * stay in the handle (rwr_evaluate_users) and are returned: test_ptr[n_users+1], test_ids[min(total, cap)] (node ids,
  * ascending per user), *n_test = total.  Output pointers may be NULL.  The reference holds out the ego user (index 0)
  * only; BASELINE config 5 holds out 100k users of one graph (n_folds = 10, fold = 9: the newest tenth).                */

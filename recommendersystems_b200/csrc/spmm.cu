@@ -29,6 +29,7 @@ struct MMCtl {
     int seed_flag[MM_MAXB];
     unsigned ticket;
     int fault;             // checked build (-DRWR_CHECKED): a gather source outside [0, n)
+    unsigned poison;       // bit j: the S_j this iteration used was NaN / Inf -> every entry of column j is NaN (k_spmm_poison)
 };
 
 template <typename T>
@@ -384,11 +385,34 @@ __global__ void __launch_bounds__(256) k_spmm_fixup(const MMParams<T> p, int mai
         for (int i = threadIdx.x / B; i < total; i += 256 / B) a += __ldcg(p.slot_S + (size_t)i * B + (threadIdx.x % B));
         sm[threadIdx.x] = a;
         __syncthreads();
+        if (threadIdx.x == 0) ctl->poison = 0;
+        __syncthreads();
         if (threadIdx.x < B) {
             double tot = 0.0;
             for (int i = threadIdx.x; i < 256; i += B) tot += sm[i];
+            // the S_j this iteration ran with: `S * 0` is NaN iff some rank of the previous vector was NaN / Inf (see k_spmm_poison)
+            if (p.seeds[threadIdx.x] >= 0 && !((ctl->S[threadIdx.x] * 0.0) == 0.0)) atomicOr(&ctl->poison, 1u << threadIdx.x);
             ctl->S[threadIdx.x] = tot;
             if (threadIdx.x == 0) ctl->ticket = 0;
+        }
+    }
+}
+
+// Model.cs:92-93 / :96-97 add `x * restart[r]` to EVERY node r.  With a one-hot restart vector that is `x * 0`: nothing, unless a
+// rank x of the previous vector is NaN or Inf (a row whose weights sum to 0, Graph.cs:81) -- then every entry of the next
+// vector is NaN in the reference.  k_spmm_fixup marks such columns; this kernel (a no-op otherwise: one word read per block)
+// overwrites them.
+template <typename T, bool WRITE_Y>
+__global__ void __launch_bounds__(256) k_spmm_poison(const MMParams<T> p) {
+    constexpr int B = Vec<T>::B;
+    const unsigned mask = p.ctl->poison;
+    if (mask == 0) return;
+    const T nan = (T)__longlong_as_double(0x7ff8000000000000LL);
+    const size_t total = (size_t)p.n * B;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (size_t)gridDim.x * 256) {
+        if ((mask >> (unsigned)(i % B)) & 1u) {
+            p.x_next[i] = nan;
+            if (WRITE_Y) p.y[i] = nan;
         }
     }
 }
@@ -401,6 +425,7 @@ __global__ void k_spmm_init(int n, MMParams<T> p, T* __restrict__ r0 /* may be n
         for (int c = 0; c < MM_MAXB; c++) { p.ctl->seed_sum[c] = 0.0; p.ctl->seed_flag[c] = 0; p.ctl->S[c] = 0.0; }
         p.ctl->ticket = 0;
         p.ctl->fault = 0;
+        p.ctl->poison = 0;
     }
     if (i >= (size_t)n * B) return;
     const int row = (int)(i / B), col = (int)(i % B);
@@ -493,12 +518,13 @@ void spmm_run_tile(rwr_graph* g, const int* seeds_int, int n_active, double c, i
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws.smem));      \
         kern<<<ws.main_grid, MM_THREADS, ws.smem, st>>>(p);                                                     \
         k_spmm_fixup<T, W><<<ws.fix_grid, 256, 0, st>>>(p, ws.main_grid);                                       \
+        k_spmm_poison<T, W><<<std::max(1, g->sm_count), 256, 0, st>>>(p);                                       \
     } while (0)
         if (valued) { if (last) MM_LAUNCH(true, true); else MM_LAUNCH(true, false); }
         else { if (last) MM_LAUNCH(false, true); else MM_LAUNCH(false, false); }
 #undef MM_LAUNCH
         KERNEL_CHECK();
-        *launches += 2;
+        *launches += 3;
         std::swap(x_cur, x_nxt);
     }
     CUDA_CHECK(cudaStreamSynchronize(st));      // the workspace goes back to the handle's scratch pool on return

@@ -981,6 +981,10 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
     const double S = ctl->S;
     const int seed = ctl->seed;
     const T uni_add = (T)((seed < 0) ? S * p.inv_n : 0.0);
+    // Model.cs:92-93 / :96-97 add `x * restart[r]` to EVERY node r: for a one-hot restart vector that is `x * 0`, nothing -- unless
+    // some rank x is NaN or Inf (a row whose weights sum to 0, Graph.cs:81): then every entry of the next vector is NaN.  S is the
+    // sum of those x, so `S * 0` is NaN exactly then.
+    const bool poisoned = seed >= 0 && !((S * 0.0) == 0.0);
     const u64 pol_first = policy_evict_first(), pol_last = policy_evict_last();
     double accS = 0.0, accR = 0.0;
     for (int row = p.row_begin + blockIdx.x * FIN_THREADS + threadIdx.x; row < p.row_end; row += gridDim.x * FIN_THREADS) {
@@ -1001,6 +1005,7 @@ __global__ void __launch_bounds__(FIN_THREADS) k_finish_ws(const IterParams<T> p
         const T invr = ld_stream(p.inv + row, pol_first);
         if (row == seed) { y = (T)__dadd_rn((double)y, S); p.y[row] = y; }
         if (seed < 0) { y = add_rn(y, uni_add); p.y[row] = y; }
+        if (poisoned && row != seed) { y = (T)(S * 0.0); p.y[row] = y; }
         if (BMODE != 0) p.y[row] = y;
         const T rw = mul_rn(p.omc, y);
         // the next iteration gathers x_next: hot rows should still be in L2 then, cold rows are streamed

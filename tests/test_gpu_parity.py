@@ -274,6 +274,48 @@ def test_empty_and_degenerate_graphs():
     assert np.isnan(g3.csr()[2]).all()
 
 
+@pytest.mark.parametrize("case", [4, 5])
+def test_nan_and_inf_rows_poison_every_node_like_the_reference(case):
+    """A row whose weights sum to 0 has NaN / Inf weights (Graph.cs:81).  The reference's restart loops add `x * restart[r]` to
+    EVERY node (Model.cs:92-93, :96-97): once a rank is NaN or Inf, `x * 0` makes the whole next vector NaN.  The oracle does
+    exactly that (held to the reference's compiled sources in tests/test_reference_pin.py, same graphs); so must both device paths."""
+    import random
+    from random_graphs import random_flat
+    rng = random.Random(20260200 + case)
+    f = random_flat(rng, rng.randrange(3, 12), rng.randrange(5, 60), rng.randrange(0, 4), rng.randrange(20, 400), zero_rows=1, nan_rows=1)
+    gg, og = gpu_graph(f), oracle_graph(f)
+    rp, col, val = gg.csr()
+    orp, ocol, oval = og.csr()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol) and np.array_equal(bits(val), bits(oval))
+    assert np.isnan(oval).any() or np.isinf(oval).any()
+    n = gg.size()
+    has_links = np.bincount(np.asarray(f["src"], np.int64), minlength=n) > 0
+    seeds = [s for s in sorted(set([0, n // 2, n - 1] + [rng.randrange(n) for _ in range(3)])) if has_links[s]]
+    poisoned_runs = 0
+    for seed in seeds:
+        for it in (1, 2, 3, 8):
+            want, _ = og.run(seed, C015, n_iter=it)
+            m = rs.Model(gg, C015, seed)
+            m.run(it)
+            nan = np.isnan(want)
+            assert np.array_equal(np.isnan(m.rank), nan), (seed, it)
+            assert np.array_equal(np.isinf(m.rank), np.isinf(want)), (seed, it)
+            ok = np.isfinite(want)
+            assert_close_fp64(m.rank[ok], want[ok], f"seed {seed} iter {it}")
+            poisoned_runs += int(nan.all())
+    assert poisoned_runs > 0                                # some run ends with every score NaN, as in the reference
+    # rankings: NaN scores sort below every number and tie among themselves -> id descending (Double.CompareTo, Recommender.cs:34-38)
+    rec = rs.Recommender(gg)
+    ids_b, sc_b, cnt_b = rec.RecommendationBatch(seeds, 0.15, 6, 10)           # the batched (SpMM) path
+    for i, seed in enumerate(seeds):
+        wi, ws = og.recommend(seed, 0.15, 6)
+        full = rec.Recommendation(seed, 0.15, 6)
+        assert [p[0] for p in full] == wi.tolist() and np.array_equal(np.isnan([p[1] for p in full]), np.isnan(ws)), seed
+        k = min(10, len(wi))
+        assert cnt_b[i] == k and ids_b[i, :k].tolist() == wi[:k].tolist() and np.array_equal(np.isnan(sc_b[i, :k]), np.isnan(ws[:k])), seed
+    gg.close()
+
+
 def test_unsorted_input_is_grouped_stably():
     g = load_golden("small_b")
     inp = g["input"]
