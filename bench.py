@@ -650,18 +650,21 @@ def c1_literal_leg():
     og.close()
     # the reference ITSELF where its compiled sources travelled with the repo (oracle/_ref/libref.so, `make -C oracle ref`):
     # Graph.cs / Model.cs / Recommender.cs as written, through oracle/cs2cpp.py -- and it must agree with the port bit for bit
-    import ref as RF
     reference = None
-    if RF.available(build=False):
-        rg = RF.ReferenceGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
-        assert rg.build() == 0
-        t0 = time.perf_counter()
-        got, _ = rg.run(seed, O.widen_float(C_FLOAT), n_iter=iters)
-        ref_s = (time.perf_counter() - t0) * N_ITER / iters
-        rg.close()
-        reference = {"kind": "reference", "how": "the reference's own Graph.cs / Model.cs compiled by g++ after oracle/cs2cpp.py respelt the "
-                     "declarations (no C# toolchain in this image)", "cpu_seconds_per_request": round(ref_s, 3),
-                     "bit_identical_to_port": bool(np.array_equal(got.view(np.uint64), want.view(np.uint64)))}
+    try:
+        import ref as RF
+        if RF.available(build=False):
+            rg = RF.ReferenceGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+            assert rg.build() == 0
+            t0 = time.perf_counter()
+            got, _ = rg.run(seed, O.widen_float(C_FLOAT), n_iter=iters)
+            ref_s = (time.perf_counter() - t0) * N_ITER / iters
+            rg.close()
+            reference = {"kind": "reference", "how": "the reference's own Graph.cs / Model.cs compiled by g++ after oracle/cs2cpp.py respelt "
+                         "the declarations (no C# toolchain in this image)", "cpu_seconds_per_request": round(ref_s, 3),
+                         "bit_identical_to_port": bool(np.array_equal(got.view(np.uint64), want.view(np.uint64)))}
+    except Exception as e:   # noqa: BLE001  (a supplementary figure must not take the bench line down)
+        reference = {"kind": "reference", "error": str(e)[:200]}
     g = rs.Graph.from_arrays(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
     g.buildGraph()
     rec = rs.Recommender(g)
