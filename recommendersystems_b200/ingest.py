@@ -83,9 +83,11 @@ class EgoNetwork:
         ego = self.ego_id
         # addMemberNodes, :256-267: the ego user, then the followees that follow back
         self.add_user(ego, NodeType.USER)
+        self._friends = 0
         for f in self.following(ego):
             if ego in set(self.following(f)):
                 self.add_user(f, NodeType.USER)
+                self._friends += 1                             # getFriendsCountOfEgoUser, :110-120 (a self-follow counts there, too)
         members = list(self.member_idx)
         # addTweetNodesAndLikeEdges, :269-307.  The ego user's likes are walked in ascending tweet id (the reference walks the
         # training part of the id-sorted list, :126-138, :289-295), every other member's in query order.
@@ -143,8 +145,8 @@ class EgoNetwork:
     def like_count(self) -> int:                               # getLikeCountOfEgoUser, :94-109
         return sum(1 for (_, t, _) in self.links[0] if t == EdgeType.LIKE)
 
-    def friends_count(self) -> int:                            # getFriendsCountOfEgoUser, :111-120
-        return len(self.member_idx) - 1
+    def friends_count(self) -> int:                            # getFriendsCountOfEgoUser, :110-120
+        return self._friends
 
     def is_valid(self, n_folds: int) -> bool:                  # checkEgoNetworkValidation, :79-92
         likes, friends = self.like_count(), self.friends_count()

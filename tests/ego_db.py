@@ -39,6 +39,19 @@ def random_tables(rng, n_friends=55, n_nonfriend_followees=6, n_third=25, n_twee
     return dict(follow=follow, tweet=tweet, mention=mention, **likes)
 
 
+def add_nasty_rows(tables, rng, ego=1000):
+    """Rows a crawler can produce and DataLoader has an answer for: self-follows, followers the ego does not follow, mentions of
+    oneself and of / by non-members, a duplicate tweet row, likes of a tweet that is not in the tweet table; all tables shuffled."""
+    m1, m2 = ego + 1, ego + 2
+    tables["follow"] += [(ego, ego), (m1, m1), (7777, ego), (m2, 7777)]
+    tables["mention"] += [(ego, ego)] * 3 + [(ego, 7777)] * 2 + [(7777, m1)] * 2 + [(m1, m2)] * 5
+    tables["tweet"] += [tables["tweet"][0], (4242, ego), (4243, m1)]
+    tables["favorite"] += [(ego, 4242), (m1, 4242), (m1, 999999), (ego, 4243)]
+    for k in tables:
+        rng.shuffle(tables[k])
+    return tables
+
+
 def write_sqlite(path, tables):
     if os.path.exists(path):
         os.remove(path)

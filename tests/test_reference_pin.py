@@ -370,3 +370,36 @@ def test_loader_graph_matches_ingest_hold_out_and_masks(tmp_path, methodology, f
     # of the ego's likes -- the members' prefix is identical
     k = int((np.asarray(ref["node_type"]) == 1).sum())
     assert ref["node_id"][:k].tolist() == links["node_id"][:k].tolist()
+
+
+@needs_ref
+@pytest.mark.parametrize("trial", range(10))
+def test_loader_fuzz(tmp_path, trial):
+    """Small and odd ego networks (few friends, 0..15 likes of the ego, 1..4 folds, self-follows, mentions of non-members, duplicate
+    rows): checkEgoNetworkValidation's counts, the test set and the graph of EVERY methodology against the reference's DataLoader."""
+    import ego_db
+    import experiment_ref as R
+    from recommendersystems_b200.ingest import load_ego_network
+    rng = random.Random(5000 + trial)
+    n_friends = rng.choice([8, 12, 20])
+    tables = ego_db.random_tables(rng, n_friends=n_friends, n_nonfriend_followees=rng.choice([0, 3]), n_third=rng.choice([2, 6]),
+                                  n_tweets=rng.choice([15, 60]), ego_likes=rng.choice([0, 3, 9, 15]))
+    if trial % 2:
+        ego_db.add_nasty_rows(tables, rng)
+    db = ego_db.write_sqlite(str(tmp_path / "1000.sqlite"), tables)
+    rdb = RF.ReferenceDb(db, tables)
+    links, net = load_ego_network(db)
+    n_folds = rng.choice([1, 2, 4])
+    assert rdb.validation(n_folds) == (net.is_valid(n_folds), net.like_count(), net.friends_count())
+    for methodology in range(16):
+        fold = rng.randrange(n_folds)
+        ref = rdb.load(n_folds, methodology, fold)
+        held, test = R.hold_out(links, [0], n_folds, fold)
+        cfg = R.apply_methodology(held, methodology)
+        if methodology in R.RETYPE_FRIENDSHIP:
+            ref["etype"] = np.where(ref["etype"] == R.FRIENDSHIP, 0, ref["etype"])
+        assert sorted(ref["test_ids"].tolist()) == test[0].tolist(), (methodology, fold)
+        a, ta = _by_id(ref)
+        b, tb = _by_id(cfg)
+        assert a == b, (methodology, fold)
+        assert set(ta) <= set(tb) and all(tb[i] == t for i, t in ta.items()), (methodology, fold)
