@@ -712,6 +712,7 @@ def run_reference(args):
         og.run_many(seeds[i * threads:(i + 1) * threads], C_FLOAT, sample_iters, threads)
     dt = time.perf_counter() - t0
     value = nnz * sample_iters * threads * args.steps / dt / 1e9
+    reference_itself = reference_on_a_scaled_graph(args.scale)
     sample = (f"each step = {threads} seeds on {threads} threads (one graph per thread, Program.cs:11/:61-66), "
               f"Model.run({sample_iters}) each ({sample_iters} of 20 iterations, no ranking), collapsed O(E+N) form, full graph")
     line = {
@@ -723,12 +724,41 @@ def run_reference(args):
         "config": c2_config(og.n, nnz, args.scale, args.gpus),
         "cpu_baseline": {"value": round(value, 4), "unit": "GTEPS", "cores": threads, "kind": "port", "sample": sample,
                          "host_cores": os.cpu_count(),
-                         "note": "the reference is C# (.NET 4.5.2); no C# toolchain in this image -> oracle port"},
+                         "note": "the reference is C# (.NET 4.5.2); no C# toolchain in this image -> oracle port (collapsed O(E+N) form: "
+                                 "the reference's own loops are O(N^2) per iteration, see reference_itself)",
+                         "reference_itself": reference_itself},
         "e2e": {"value": round(value, 4), "unit": "GTEPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "build": {"setup_wall_s": round(setup_s, 2)},
     }
     print(json.dumps(line), flush=True)
+
+
+def reference_on_a_scaled_graph(scale: float):
+    """The reference's OWN Model.cs (compiled from its sources, oracle/_ref/libref.so) on the C2 generator scaled down 1000 x:
+    what its literal restart loops (Model.cs:92-93, O(N^2) per iteration) do to the metric, and why the arm above runs the
+    collapsed port -- one iteration of the literal form on the full C2 graph is 1.2e14 multiply-adds."""
+    try:
+        import numpy as np
+        import oracle as O
+        import ref as RF
+        if not RF.available(build=False):
+            return None
+        links = O.synth_generate(scaled_spec(scale * 1e-3))
+        rg = RF.ReferenceGraph(links["node_id"], links["node_type"], links["src"], links["dst"], links["etype"], links["w"])
+        assert rg.build() == 0
+        seed = int(np.flatnonzero(np.bincount(links["src"], minlength=rg.n) > 0)[0])
+        t0 = time.perf_counter()
+        rg.run(seed, O.widen_float(C_FLOAT), n_iter=2)
+        dt = time.perf_counter() - t0
+        nnz, n = rg.nnz(), rg.n
+        rg.close()
+        return {"kind": "reference", "how": "Graph.cs / Model.cs compiled by g++ after oracle/cs2cpp.py respelt the declarations",
+                "workload": f"the C2 generator at 1/1000 of the size: {n} nodes, {nnz} links, Model.run(2), 1 thread",
+                "gteps": round(nnz * 2 / dt / 1e9, 6), "seconds": round(dt, 3),
+                "extrapolated_seconds_per_iteration_at_full_size": round(dt / 2 * 1e6, 0)}
+    except Exception as e:   # noqa: BLE001
+        return {"kind": "reference", "error": str(e)[:200]}
 
 
 def main():
