@@ -6,7 +6,9 @@
 No C# toolchain exists here (mono, mcs, csc, dotnet, msbuild: all absent), so the reference cannot be built the usual way.
 Its RWR path and the callers either side of it, however, are a few hundred lines of a C# subset whose statements are also
 C++ statements once the declarations are respelt.  This script reads the sources WHERE THEY LIE under /root/reference and
-writes C++ headers into oracle/_ref/ (git-ignored; reference text never enters the repository):
+writes two C++ headers into a TEMPORARY directory that `make -C oracle ref` deletes once g++ has consumed them: only the
+binaries (oracle/_ref/libref.so, caller_reference) and the SHA-256 list of the sources stay, git-ignored; reference text never
+enters the repository or its working tree:
 
   reference_rwr.hpp         Recommenders/RWRBased/{Graph,Model,Recommender}.cs, whole            (the hot path)
   reference_experiment.hpp  TweetRecommender/DataLoader.cs, whole; of Experiment.cs the enums, ThreadParams and the k-fold
@@ -35,7 +37,7 @@ knows what the code computes, and no arithmetic expression, loop bound, comparis
   order          top-level types are emitted enums first, then structs, then classes in dependency order (C++ needs a
                  type complete before its first use; C# does not)
 
-The headers record the SHA-256 of each source file they were made from.  tests/test_reference_pin.py checks the translator on
+oracle/_ref/sources.sha256 records the SHA-256 of each source file the library was made from.  tests/test_reference_pin.py checks the translator on
 its own rule table (no reference needed) and, where oracle/_ref/libref.so exists, holds the C++ oracle, the Python
 restatements and the committed golden vectors to the transliterated reference.
 """
@@ -172,7 +174,7 @@ def header(files: dict, includes) -> list:
     return out + [""]
 
 
-def transliterate(files: dict, includes=("../ref_shim.hpp",), known_namespaces=(), known_enums=(), external_classes=(),
+def transliterate(files: dict, includes=("ref_shim.hpp",), known_namespaces=(), known_enums=(), external_classes=(),
                   known_structs=(), only=None, fragments=()) -> str:
     """files: {relative path: C# text} -> the C++ header text.
     only:       {file: set of top-level type names to emit}; a file that is not a key is emitted whole
@@ -241,7 +243,7 @@ def transliterate_rwr(ref_root: str) -> str:
 
 def transliterate_callers(ref_root: str) -> str:
     return transliterate(
-        read_sources(ref_root, CALLER_SOURCES), includes=("../ref_shim.hpp", "reference_rwr.hpp"),
+        read_sources(ref_root, CALLER_SOURCES), includes=("ref_shim.hpp", "reference_rwr.hpp"),
         known_namespaces=("Recommenders.RWRBased",), known_enums=("NodeType", "EdgeType"),
         external_classes=("SQLiteAdapter", "Graph", "Model", "Recommender"), known_structs=("Node", "ForwardLink"),
         only={"TweetRecommender/Experiment.cs": {"Methodology", "Feature", "EvaluationMetric", "ThreadParams"}},
@@ -252,13 +254,18 @@ def transliterate_callers(ref_root: str) -> str:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", default="/root/reference")
-    ap.add_argument("--out-dir", default=os.path.join(HERE, "_ref"))
+    ap.add_argument("--out-dir", default=os.path.join(HERE, "_ref"), help="where the generated headers go (the Makefile passes a temporary directory)")
+    ap.add_argument("--hashes", default=None, help="write `sha256  file` of every source read (kept next to libref.so)")
     args = ap.parse_args()
     os.makedirs(args.out_dir, exist_ok=True)
     for name, text in (("reference_rwr.hpp", transliterate_rwr(args.ref)), ("reference_experiment.hpp", transliterate_callers(args.ref))):
         with open(os.path.join(args.out_dir, name), "w") as f:
             f.write(text)
         print("wrote %s (%d lines)" % (os.path.join(args.out_dir, name), text.count("\n")))
+    if args.hashes:
+        with open(args.hashes, "w") as f:
+            for rel, text in {**read_sources(args.ref, SOURCES), **read_sources(args.ref, CALLER_SOURCES)}.items():
+                f.write("%s  %s\n" % (hashlib.sha256(text.encode("utf-8")).hexdigest(), rel))
 
 
 if __name__ == "__main__":

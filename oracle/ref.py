@@ -16,7 +16,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref.so")
-HEADER_PATHS = (os.path.join(_HERE, "_ref", "reference_rwr.hpp"), os.path.join(_HERE, "_ref", "reference_experiment.hpp"))
+HASHES_PATH = os.path.join(_HERE, "_ref", "sources.sha256")
 REFERENCE_ROOT = "/root/reference"
 _LIB = None
 
@@ -62,14 +62,12 @@ def lib() -> C.CDLL:
 
 
 def source_hashes() -> dict:
-    """{reference file: sha256} as recorded in the generated header (what libref.so was made from)."""
+    """{reference file: sha256} of the sources libref.so was made from (written next to it by `make -C oracle ref`)."""
     out = {}
-    for path in HEADER_PATHS:
-        with open(path) as f:
-            for line in f:
-                if line.startswith("// source: "):
-                    _, _, rel, _, h = line.split()
-                    out[rel] = h
+    with open(HASHES_PATH) as f:
+        for line in f:
+            h, rel = line.split()
+            out[rel] = h
     return out
 
 

@@ -1,9 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- the product path (recommendersystems_b200/, librwr_b200.so) never links, loads or calls this.
 //
-// C ABI over the reference's OWN classes: oracle/_ref/reference_rwr.hpp is Recommenders/RWRBased/{Graph,Model,Recommender}.cs
-// and oracle/_ref/reference_experiment.hpp is TweetRecommender/DataLoader.cs + the k-fold loop of Experiment.cs, as
-// oracle/cs2cpp.py respells them for a C++ compiler (built from the sources where they lie under /root/reference; the
-// headers are git-ignored and never committed).  This file only does what the reference's callers do
+// C ABI over the reference's OWN classes: reference_rwr.hpp is Recommenders/RWRBased/{Graph,Model,Recommender}.cs and
+// reference_experiment.hpp is TweetRecommender/DataLoader.cs + the k-fold loop of Experiment.cs, as oracle/cs2cpp.py respells
+// them for a C++ compiler (generated from the sources where they lie under /root/reference into a temporary directory that
+// the Makefile deletes after the build: reference text never stays in the tree).  This file only does what the reference's callers do
 // (TweetRecommender/DataLoader.cs:60-77 fills `allNodes` / `allLinks`, Experiment.cs:104-109 builds the graph and asks for a
 // recommendation, Experiment.cs:61-66 sets up the result dictionary) and copies the results out; it contains no arithmetic
 // of the path.
@@ -12,8 +12,8 @@
 #include <cstdint>
 #include <cstring>
 
-#include "_ref/reference_rwr.hpp"
-#include "_ref/reference_experiment.hpp"
+#include "reference_rwr.hpp"           // generated into a temporary directory by `make -C oracle ref` (-I), deleted after the build
+#include "reference_experiment.hpp"
 
 using namespace Recommenders_RWRBased;
 using TweetRecommender::DataLoader;

@@ -1,6 +1,6 @@
 """The C++ host side of the drop-in (recommendersystems_b200/cpp/RWRBased.hpp) through ONE caller compiled twice
 (experiment_caller.cpp): against RWRBased.hpp over librwr_b200.so (caller_b200) and against the reference's own sources as
-oracle/cs2cpp.py respells them (oracle/_ref/caller_reference).  Same caller text, same graphs: the printed recommendation lists
+oracle/cs2cpp.py respells them (oracle/_ref/caller_reference, built by `make -C oracle ref`).  Same caller text, same graphs: the printed recommendation lists
 must be identical and the scores agree to 1e-12 (exact zeros preserved).  Without a GPU caller_b200 must fail loudly."""
 import os
 import subprocess
@@ -17,7 +17,9 @@ REFERENCE = os.path.join(ROOT, "oracle", "_ref", "caller_reference")
 
 
 def build():
+    import ref as RF
     subprocess.check_call(["make", "-C", CPP, "-s"])
+    RF.available()                  # `make -C oracle ref` where the reference's sources are: builds caller_reference, too
 
 
 def write_graph(path, inp):

@@ -2,7 +2,7 @@
 
 No C# toolchain exists in this image, so `make -C oracle ref` compiles Recommenders/RWRBased/{Graph,Model,Recommender}.cs
 from where they lie under /root/reference after oracle/cs2cpp.py has respelt their declarations for a C++ compiler
-(oracle/_ref/libref.so; nothing of the reference is committed).  Here:
+(oracle/_ref/libref.so; the respelt text lives in a temporary directory during the build, nothing of the reference stays).  Here:
   * the translator's rules are checked on a C# text written for this test (runs anywhere, needs no reference);
   * where libref.so exists, the transliterated reference must reproduce every committed golden vector bit for bit, and the
     hand-written oracle (literal and collapsed forms) must agree with it bit for bit on random graphs with the corner cases
