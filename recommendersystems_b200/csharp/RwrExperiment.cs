@@ -19,7 +19,9 @@ namespace Recommenders.RWRBased {
         }
 
         // DataLoader.splitLikeHistory (DataLoader.cs:122-140) for `users`, applied by the next buildGraph() of `graph`;
-        // testSets[i] receives users[i]'s held-out tweet ids (`loader.testSet`)
+        // testSets[i] receives users[i]'s held-out tweet ids (`loader.testSet`).  A held-out tweet nobody else likes is no node
+        // of the graph DataLoader would have built (:291-303, :355-356): the native side drops its remaining links and makes
+        // it no candidate, so HIT and AVGPRECISION are those of a reload
         public static void HoldOut(Graph graph, int[] users, int nFolds, int fold, List<long>[] testSets) {
             graph.beforeBuild = g => {
                 var ptr = new long[users.Length + 1];

@@ -30,7 +30,17 @@ def result_row(ego_id: int, methodology: int, n_folds: int, n_iter: int, hits: f
     """One line of result.dat (Experiment.cs:144-152; read back as 7 tab-separated tokens at Program.cs:41):
     ego \\t methodology \\t nFolds \\t nIterations \\t (int)HIT \\t cntLikes \\t AVGPRECISION / nFolds."""
     return "\t".join([str(int(ego_id)), str(int(methodology)), str(int(n_folds)), str(int(n_iter)), str(int(hits)),
-                      str(int(cnt_likes)), "%.15g" % (sum_ap / n_folds)])      # .NET double.ToString() == "G15"
+                      str(int(cnt_likes)), dotnet_double_to_string(sum_ap / n_folds)])
+
+
+def dotnet_double_to_string(x: float) -> str:
+    """`"\\t" + double` on .NET Framework (Experiment.cs:150): double.ToString() is the "G15" format -- 15 significant digits,
+    fixed notation while -5 < exponent < 15, else scientific with an upper-case E and at least two exponent digits."""
+    if x != x:
+        return "NaN"
+    if x in (float("inf"), float("-inf")):
+        return "Infinity" if x > 0 else "-Infinity"
+    return ("%.15g" % x).replace("e", "E")      # C's %g switches notation at the same exponents and pads the exponent alike
 
 
 def run_k_fold(links: Dict[str, np.ndarray], methodology: int = Methodology.ALL, n_folds: int = 10, n_iter: int = 20,

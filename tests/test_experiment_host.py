@@ -92,6 +92,10 @@ def test_result_row_format_and_like_count():
     assert like_count(_tiny(), 0) == 5 and like_count(_tiny(), 1) == 2
     row = result_row(12345, 8, 10, 20, 7.0, 93, 1.2345678901234567)
     assert row.split("\t") == ["12345", "8", "10", "20", "7", "93", "0.123456789012346"]       # G15, Program.cs:41 reads 7 tokens
+    from recommendersystems_b200.experiment import dotnet_double_to_string as fmt
+    # .NET Framework's double.ToString(): fixed notation down to 1e-5 exclusive, then `E-05`; integers without a point
+    assert [fmt(v) for v in (0.0, 1.0, 0.5, 0.0001, 0.00001, 1.5e-7, 123456789012345678.0, float("nan"))] == \
+        ["0", "1", "0.5", "0.0001", "1E-05", "1.5E-07", "1.23456789012346E+17", "NaN"]
 
 
 def test_reference_evaluate_arithmetic():
