@@ -228,6 +228,37 @@ def test_oracle_matches_the_reference_on_random_graphs(case):
 
 
 @needs_ref
+def test_oracle_matches_the_reference_on_many_small_graphs():
+    """Breadth: 80 more random graphs (a third of them with NaN / Inf rows), one seed and three iteration counts each, both forms of
+    the oracle, the full recommendation list -- all bit for bit."""
+    c = O.widen_float(0.15)
+    compared = 0
+    for case in range(80):
+        rng = random.Random(77000 + case)
+        poisoned = case % 3 == 0
+        f = random_flat(rng, rng.randrange(2, 8), rng.randrange(3, 30), rng.randrange(0, 3), rng.randrange(5, 150),
+                        zero_rows=int(poisoned), nan_rows=int(poisoned and case % 2 == 0))
+        args = (f["node_id"], f["node_type"], f["src"], f["dst"], f["etype"], f["w"])
+        rg, og = RF.ReferenceGraph(*args), O.OracleGraph(*args)
+        assert rg.build() == 0 and og.build() == 0
+        for a, b in zip(rg.csr(), og.csr()):
+            assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), case
+        with_links = np.flatnonzero(np.bincount(np.asarray(f["src"], np.int64), minlength=rg.n) > 0)
+        seed = int(with_links[rng.randrange(len(with_links))]) if len(with_links) else 0
+        for it in (1, 3, 11):
+            want, _ = rg.run(seed, c, n_iter=it)
+            for literal in (True, False):
+                assert np.array_equal(bits(og.run(seed, c, n_iter=it, literal=literal)[0]), bits(want)), (case, it, literal)
+        if len(with_links):
+            wi, ws = rg.recommend(seed, 0.15, 4)
+            gi, gs = og.recommend(seed, 0.15, 4)
+            assert wi.tolist() == gi.tolist() and np.array_equal(bits(ws), bits(gs)), case
+            compared += 1
+        rg.close(); og.close()
+    assert compared >= 75
+
+
+@needs_ref
 def test_reference_exceptions_of_the_boundary():
     """IndexOutOfRangeException for a link target >= N (Model.cs:87), KeyNotFoundException before buildGraph()
     (Model.cs:79) and for a seed without an `edges` entry (Recommender.cs:21); an entry that exists but is empty is fine."""
