@@ -42,6 +42,7 @@ class EgoNetwork:
         self.member_idx: Dict[int, int] = {}
         self.tweet_idx: Dict[int, int] = {}
         self._seen: List[set] = []
+        self._friends = 0
 
     # ---- SQLiteAdapter.cs ---------------------------------------------------------------------------------------
     def following(self, user: int) -> List[int]:               # getFollowingUsers, SQLiteAdapter.cs:27-40
