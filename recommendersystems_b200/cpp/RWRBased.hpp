@@ -12,8 +12,8 @@
 //     auto recommendation = recommender.Recommendation(0, 0.15f, nIterations);      // List<KeyValuePair<long, double>>
 //
 // (or, spelt the way oracle/cs2cpp.py respells C# class references: `Graph* graph = new Graph(nodes, edges); graph->buildGraph();
-// Recommender* recommender = new Recommender(graph);` -- experiment_caller.cpp compiles ONE such caller against this header and
-// against the reference's own sources and must print the same lists.)
+// Recommender* recommender = new Recommender(graph);` -- tests/cpp/experiment_caller.cpp is ONE such caller, compiled against this
+// header and against the reference's own sources; the two programs must print the same lists.)
 //
 // Header only; link with -lrwr_b200.  Nothing is computed here: flattening `edges` in `for i in 0..N-1: foreach l in edges[i]`
 // order (rwr_graph_create's input contract), widening `float dampingFactor` to double exactly as Recommender.cs:16 does, and

@@ -24,8 +24,8 @@ def pytest_sessionstart(session):
     pkg = os.path.join(ROOT, "recommendersystems_b200")
     if not os.path.exists(os.path.join(pkg, "librwr_b200.so")):
         subprocess.check_call(["make", "-C", os.path.join(pkg, "csrc"), "-j8", "-s"])
-    if not os.path.exists(os.path.join(pkg, "cpp", "caller_b200")):
-        subprocess.check_call(["make", "-C", os.path.join(pkg, "cpp"), "-s"])
+    if not os.path.exists(os.path.join(ROOT, "tests", "cpp", "caller_b200")):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "tests", "cpp"), "-s"])
 
 
 def unhex(xs):

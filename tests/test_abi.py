@@ -47,9 +47,10 @@ def test_no_torch_types_and_no_oracle_in_product():
     pkg = os.path.join(ROOT, "recommendersystems_b200")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h", ".cs")):
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cs", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "liboracle" not in text and "import oracle" not in text and "rwr_literal" not in text, f
+                assert "libref" not in text and "ref_shim" not in text and "reference_rwr" not in text and "import ref" not in text, f
     import subprocess
     out = subprocess.run(["ldd", N.LIB_PATH], capture_output=True, text=True).stdout
     assert "oracle" not in out and "torch" not in out

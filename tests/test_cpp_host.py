@@ -1,5 +1,5 @@
 """The C++ host side of the drop-in (recommendersystems_b200/cpp/RWRBased.hpp) through ONE caller compiled twice
-(experiment_caller.cpp): against RWRBased.hpp over librwr_b200.so (caller_b200) and against the reference's own sources as
+(tests/cpp/experiment_caller.cpp): against RWRBased.hpp over librwr_b200.so (caller_b200) and against the reference's own sources as
 oracle/cs2cpp.py respells them (oracle/_ref/caller_reference, built by `make -C oracle ref`).  Same caller text, same graphs: the printed recommendation lists
 must be identical and the scores agree to 1e-12 (exact zeros preserved).  Without a GPU caller_b200 must fail loudly."""
 import os
@@ -11,7 +11,7 @@ import pytest
 from conftest import C1_SPEC, ROOT, bits, load_golden, unhex
 import oracle as O
 
-CPP = os.path.join(ROOT, "recommendersystems_b200", "cpp")
+CPP = os.path.join(ROOT, "tests", "cpp")
 B200 = os.path.join(CPP, "caller_b200")
 REFERENCE = os.path.join(ROOT, "oracle", "_ref", "caller_reference")
 
